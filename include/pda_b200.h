@@ -1,0 +1,182 @@
+/* pda_b200 -- C ABI of the B200-native PDA hot path (libpda_b200.so, sm_100a only).
+ *
+ * What this replaces in the reference (zyang1580/PDA; paths relative to its root):
+ * the TF1 session objects behind MF/train_new_api.py -- the model graph of MF/model_api.py
+ * (BPRMF :419-471,695-706; ConditionalBPRMF :19-134), the sampler generators
+ * (MF/train_new_api.py:260-456), the inference graph (Create_Recommendation :594-612,
+ * do_recommendation :614-640, testing :642-669, predict :683-696), the metric code
+ * (MF/used_metric.py:39-80) and, for NeuRec-style callers, the native evaluator entry points
+ * cpp_evaluate_matrix (evaluator/backend/cpp/include/evaluate.h:53) and arg_top_k_2d
+ * (util/cython/include/arg_topk.h:29).  INTEGRATION.md shows the ctypes binding a maintainer
+ * of the reference would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on error; pda_last_error() gives the text
+ *     of the calling thread's last error.  No exceptions cross the ABI, no ownership transfer:
+ *     buffers passed in are only read/written during the call.
+ *   - a pda_model owns all device state of one GPU (tables, Adam slots, train CSR, popularity
+ *     tables, batch buffers).  One model per GPU/process; calls on one model are not
+ *     thread-safe (the reference's sess.run loop is single-threaded as well).
+ *   - *_host entry points take HOST pointers, copy in/out inside the call and return after the
+ *     result is on the host (the sess.run contract).  *_device entry points take DEVICE
+ *     pointers, enqueue on `stream` (a cudaStream_t passed as void*; NULL = default stream)
+ *     and return without synchronising.
+ *   - there is no CPU fallback: without a CUDA device pda_create fails with PDA_ERR_CUDA.
+ */
+#ifndef PDA_B200_H
+#define PDA_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDA_OK 0
+#define PDA_ERR_ARG 1
+#define PDA_ERR_CUDA 2
+#define PDA_ERR_STATE 3
+
+/* --train of MF/parse.py:11 */
+#define PDA_TRAIN_NORMAL 0      /* BPRMF           : create_bpr_loss                (model_api.py:695-706) */
+#define PDA_TRAIN_S_CONDITION 1 /* PD / PDA / PDG  : create_bpr_loss_with_pop_global (model_api.py:102-121) */
+
+/* rec_type of do_recommendation (train_new_api.py:626-633) */
+#define PDA_REC_MAIN_BRANCH 0   /* y = u.i                      (PD, BPRMF)   */
+#define PDA_REC_WITH_POP 1      /* y = (elu(u.i)+1) * pop[i]    (PDA 'condition', BPRMF-A 'main_with_pop') */
+
+/* table selectors for pda_get_table / pda_set_table / pda_table_ptr */
+#define PDA_TABLE_USER 0
+#define PDA_TABLE_ITEM 1
+#define PDA_TABLE_USER_M 2
+#define PDA_TABLE_USER_V 3
+#define PDA_TABLE_ITEM_M 4
+#define PDA_TABLE_ITEM_V 5
+
+/* eval back end */
+#define PDA_EVAL_AUTO 0
+#define PDA_EVAL_EXACT 1        /* CUDA-core exact scorer over all items */
+#define PDA_EVAL_TENSOR 2       /* tcgen05 bf16 filter + exact rescoring of the certified candidates */
+
+typedef struct pda_model pda_model;
+
+typedef struct pda_config {
+    int32_t device;      /* CUDA ordinal */
+    int64_t n_users;     /* data_config['n_users'] */
+    int64_t n_items;     /* data_config['n_items'] */
+    int32_t embed_size;  /* --embed_size (multiple of 4, <= 512) */
+    int32_t train_mode;  /* PDA_TRAIN_* */
+    int32_t batch_size;  /* --batch_size: divisor of the L2 term (model_api.py:118,128) and batch capacity */
+    float lr;            /* --lr */
+    float regs;          /* --regs */
+    int64_t max_batch;   /* capacity of the internal batch buffers (0 -> batch_size) */
+} pda_config;
+
+const char* pda_last_error(void);
+int pda_version(void);
+int pda_device_count(void);
+
+/* model life cycle -- replaces ConditionalBPRMF/BPRMF.__init__ + tf.Session + initializer */
+int pda_create(const pda_config* cfg, pda_model** out);
+void pda_destroy(pda_model* m);
+/* Xavier-uniform tables from the Philox stream (model_api.py:86-99); zero Adam slots; beta powers reset */
+int pda_init_tables(pda_model* m, uint32_t seed);
+int pda_set_table(pda_model* m, int which, const float* host_src);
+int pda_get_table(pda_model* m, int which, float* host_dst);
+void* pda_table_ptr(pda_model* m, int which);                 /* device pointer, row-major [rows, d] fp32 */
+int pda_get_adam_powers(pda_model* m, float* b1p_b2p_host);   /* beta1_power, beta2_power */
+int pda_set_adam_powers(pda_model* m, const float* b1p_b2p_host);
+int pda_synchronize(pda_model* m);
+
+/* per-kernel device timing with CUDA events recorded on the launching stream around each kernel:
+ * kinds PDA_PROF_*; pda_profile_read synchronises, returns the summed milliseconds and launch count
+ * per kind since the last read (arrays of PDA_PROF_KINDS) and resets the counters. */
+#define PDA_PROF_SAMPLER 0
+#define PDA_PROF_STEP 1
+#define PDA_PROF_ADAM 2
+#define PDA_PROF_EVAL 3
+#define PDA_PROF_EVAL_TC 4
+#define PDA_PROF_KINDS 5
+int pda_profile_enable(pda_model* m, int on);
+int pda_profile_read(pda_model* m, double* ms_sum, int32_t* count);
+
+/* pinned host memory for callers that want true async H2D/D2H (cudaHostAlloc / cudaFreeHost) */
+void* pda_host_alloc(int64_t bytes);
+void pda_host_free(void* p);
+
+/* training data -- replaces Data/Data2.train_user_list (+ item times) and add_expo_popularity.
+ * CSR over user ids: indptr[n_users+1], items sorted ascending within each row, times (stage of
+ * each interaction, may be NULL), unique_times = data.unique_times (may be NULL).
+ * Also the train-item mask of the recommender (train_new_api.py:730-733). */
+int pda_set_train_csr(pda_model* m, const int64_t* indptr, const int32_t* items, const uint8_t* times, int64_t nnz,
+                      const int32_t* unique_times, int32_t n_times);
+/* same, from DEVICE arrays already sorted by the caller (no validation; used for large synthetic sets);
+ * active_d = ascending ids of users with at least one interaction; unique_times is a HOST pointer */
+int pda_set_train_csr_device(pda_model* m, const int64_t* indptr_d, const int32_t* items_d, const uint8_t* times_d,
+                             int64_t nnz, const int32_t* active_d, int64_t n_act, const int32_t* unique_times,
+                             int32_t n_times);
+/* P = pop[:, :-1] ** gamma as fp32 [n_items, T_pop] (train_new_api.py:988-990); T_pop == 1 -> PDG */
+int pda_set_train_pop(pda_model* m, const float* pop, int32_t T_pop);
+
+/* sampler -- replaces generator_n_batch / generator_n_batch_with_pop (train_new_api.py:260-412).
+ * Fills the model's internal batch buffers on the device. */
+int pda_sample_batch(pda_model* m, uint32_t seed, uint32_t epoch, uint32_t step, int64_t B, void* stream);
+/* copy the internal batch to the host (any pointer may be NULL) */
+int pda_get_batch(pda_model* m, int64_t B, int32_t* users, int32_t* pos, int32_t* neg, int32_t* time, float* pos_pop,
+                  float* neg_pop);
+
+/* one optimisation step -- replaces sess.run([opt, loss, mf_loss, reg_loss]) (train_new_api.py:1080-1090).
+ * loss3_out = {loss, mf_loss, reg_loss}.  pos_pop/neg_pop are ignored for PDA_TRAIN_NORMAL. */
+int pda_train_step_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
+                        const float* pos_pop, const float* neg_pop, int64_t B, float* loss3_out);
+/* device pointers; users == NULL -> use the internal batch written by pda_sample_batch */
+int pda_train_step_device(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
+                          const float* pos_pop, const float* neg_pop, int64_t B, void* stream);
+/* n_steps x (sample + step) enqueued back to back; the loss of every step is kept on the device */
+int pda_train_steps_sampled(pda_model* m, uint32_t seed, uint32_t epoch, uint32_t step0, int32_t n_steps, int64_t B,
+                            void* stream);
+/* The step in two halves, for data-parallel callers that reduce gradients between them:
+ * pda_forward_backward_device = the fused kernel only (gradients stay in the accumulators returned by
+ * pda_grad_ptr, loss partial sums in pda_loss_acc_ptr: double[2]); pda_adam_apply = Adam sweep + loss /
+ * beta-power bookkeeping.  pda_set_global_batch(Bg > 0) makes the loss mean and the gradient scale use Bg
+ * (the batch summed over all ranks) instead of the local B.  pda_stage_batch_host copies a host batch into
+ * the internal batch buffers (then pass users == NULL). */
+int pda_set_global_batch(pda_model* m, int64_t global_batch);
+void* pda_grad_ptr(pda_model* m, int which);
+void* pda_loss_acc_ptr(pda_model* m);
+int pda_forward_backward_device(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
+                                const float* pos_pop, const float* neg_pop, int64_t B, void* stream);
+int pda_adam_apply(pda_model* m, void* stream);
+int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
+                         const float* pos_pop, const float* neg_pop, int64_t B, void* stream);
+/* loss3 of the last enqueued step (synchronises `stream`) */
+int pda_read_loss(pda_model* m, float* loss3_out, void* stream);
+/* forward/backward only (no optimizer): gradients of the two tables as dense [rows, d] host arrays; test hook */
+int pda_gradients_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
+                       const float* pos_pop, const float* neg_pop, int64_t B, float* gU_out, float* gI_out,
+                       float* loss3_out);
+
+/* recommendation -- replaces do_recommendation (train_new_api.py:614-640).  users: M global user ids;
+ * all n_items are scored; pop: fp32 [n_items] (PDA_REC_WITH_POP) or NULL; col_bias: optional fp32
+ * [n_items] added in PDA_REC_MAIN_BRANCH (BPR(t)-pop item bias, model_api.py:387); use_mask != 0
+ * removes each user's train items (the CSR of pda_set_train_csr).  ids_out int32 [M,K] sorted by
+ * (score desc, id asc) -- tf.nn.top_k's order; scores_out fp32 [M,K] or NULL.  K <= 128. */
+int pda_recommend_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop,
+                       const float* col_bias, int use_mask, int K, int backend, int32_t* ids_out, float* scores_out);
+int pda_recommend_device(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop,
+                         const float* col_bias, int use_mask, int K, int backend, int32_t* ids_out, float* scores_out,
+                         void* stream);
+/* dense scores -- replaces testing()/predict() (train_new_api.py:642-696): out fp32 [M, n_items], no mask */
+int pda_scores_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop, float* out);
+
+/* metrics -- replaces test_one_batch/get_performance (train_new_api.py:741-758, used_metric.py:69-80).
+ * ids int32 [M,Kkeep] (host), truth CSR over global user ids (host).  out double [4, nK]:
+ * precision, recall, ndcg, hit_ratio SUMMED over the M users (the caller divides). */
+int pda_metrics_host(pda_model* m, const int32_t* ids, int64_t M, int Kkeep, const int32_t* eval_users,
+                     const int64_t* truth_indptr, const int32_t* truth_items, int64_t n_truth_rows, const int32_t* Ks,
+                     int nK, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDA_B200_H */

@@ -1,0 +1,704 @@
+// C-ABI layer of libpda_b200.so: model handle, device state, host<->device staging.
+// See include/pda_b200.h for the contract and the reference interfaces each entry point replaces.
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/pda_b200.h"
+#include "pda_kernels.h"
+
+#define PDA_PROF_SLOTS 1024
+
+using namespace pda;
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(PDA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct pda_model {
+    pda_config cfg;
+    int64_t nU, nI;
+    int d;
+    float *W[2], *Mo[2], *Vo[2], *G[2];   // 0 = user table, 1 = item table
+    float* pw;          // {beta1_power, beta2_power}
+    double* loss_acc;   // {sum log(sigmoid+1e-10), sum of squares}
+    float* loss3;       // device {loss, mf, reg}
+    float* loss3_pinned;
+    // train CSR / mask
+    int64_t* indptr; int32_t* items; uint8_t* times; int64_t nnz;
+    int32_t* active; int64_t n_act;
+    int32_t* unique_times; int32_t n_times;
+    float* pop_train; int32_t T_pop;
+    // batch buffers
+    int64_t cap, last_B, global_batch;
+    int batch_uniq;   // internal batch holds distinct users (device sampler with B <= #active users)
+    int32_t *b_users, *b_pos, *b_neg, *b_time;
+    float *b_pp, *b_np;
+    void* stage_pinned; size_t stage_bytes;
+    // eval scratch
+    void* ev_buf; size_t ev_bytes;
+    void* ev_pinned; size_t ev_pinned_bytes;
+    // optional per-kernel CUDA-event timing (pda_profile_*): [kernel kind][slot][begin/end]
+    int prof_on; int prof_n[PDA_PROF_KINDS];
+    cudaEvent_t (*prof_ev)[PDA_PROF_SLOTS][2];
+};
+
+struct ProfScope {   // records an event pair around one kernel launch on the launching stream
+    pda_model* m; int kind; cudaStream_t st; int slot;
+    ProfScope(pda_model* m_, int kind_, cudaStream_t st_) : m(m_), kind(kind_), st(st_), slot(-1) {
+        if (m->prof_on && m->prof_ev && m->prof_n[kind] < PDA_PROF_SLOTS) {
+            slot = m->prof_n[kind]++;
+            cudaEventRecord(m->prof_ev[kind][slot][0], st);
+        }
+    }
+    ~ProfScope() { if (slot >= 0) cudaEventRecord(m->prof_ev[kind][slot][1], st); }
+};
+
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t n) { return cudaMalloc((void**)p, n * sizeof(T) > 0 ? n * sizeof(T) : 16); }
+
+static cudaError_t ensure_dev(void** buf, size_t* have, size_t need) {
+    if (*have >= need) return cudaSuccess;
+    if (*buf) cudaFree(*buf);
+    *buf = nullptr; *have = 0;
+    cudaError_t e = cudaMalloc(buf, need);
+    if (e == cudaSuccess) *have = need;
+    return e;
+}
+static cudaError_t ensure_pinned(void** buf, size_t* have, size_t need) {
+    if (*have >= need) return cudaSuccess;
+    if (*buf) cudaFreeHost(*buf);
+    *buf = nullptr; *have = 0;
+    cudaError_t e = cudaHostAlloc(buf, need, cudaHostAllocDefault);
+    if (e == cudaSuccess) *have = need;
+    return e;
+}
+
+extern "C" {
+
+const char* pda_last_error(void) { return g_err; }
+int pda_version(void) { return 100; }
+int pda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void* pda_host_alloc(int64_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, (size_t)bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void pda_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int pda_create(const pda_config* cfg, pda_model** out) {
+    if (!cfg || !out) return fail(PDA_ERR_ARG, "pda_create: null argument");
+    if (cfg->embed_size % 4 != 0 || cfg->embed_size < 4 || cfg->embed_size > 512)
+        return fail(PDA_ERR_ARG, "embed_size must be a multiple of 4 in [4, 512], got %d", cfg->embed_size);
+    if (cfg->n_users < 1 || cfg->n_items < 1 || cfg->batch_size < 1)
+        return fail(PDA_ERR_ARG, "n_users, n_items and batch_size must be positive");
+    if (cfg->n_users > 0x7fffffffLL || cfg->n_items > 0x7fffffffLL)
+        return fail(PDA_ERR_ARG, "ids are int32: n_users/n_items must be < 2^31");
+    if (cfg->train_mode != PDA_TRAIN_NORMAL && cfg->train_mode != PDA_TRAIN_S_CONDITION)
+        return fail(PDA_ERR_ARG, "unknown train_mode %d", cfg->train_mode);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(PDA_ERR_CUDA, "no CUDA device: pda_b200 has no CPU fallback (%s)", cudaGetErrorString(e));
+    }
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major != 10)
+        return fail(PDA_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", cfg->device, prop.major,
+                    prop.minor);
+    pda_model* m = new (std::nothrow) pda_model();
+    if (!m) return fail(PDA_ERR_STATE, "out of host memory");
+    memset(m, 0, sizeof(*m));
+    m->cfg = *cfg;
+    m->nU = cfg->n_users; m->nI = cfg->n_items; m->d = cfg->embed_size;
+    m->cap = cfg->max_batch > 0 ? cfg->max_batch : cfg->batch_size;
+    const int64_t rows[2] = {m->nU, m->nI};
+    for (int t = 0; t < 2; ++t) {
+        size_t n = (size_t)rows[t] * m->d;
+        CK(dmalloc(&m->W[t], n)); CK(dmalloc(&m->Mo[t], n)); CK(dmalloc(&m->Vo[t], n)); CK(dmalloc(&m->G[t], n));
+        CK(cudaMemset(m->W[t], 0, n * 4)); CK(cudaMemset(m->Mo[t], 0, n * 4));
+        CK(cudaMemset(m->Vo[t], 0, n * 4)); CK(cudaMemset(m->G[t], 0, n * 4));
+    }
+    CK(dmalloc(&m->pw, 2)); CK(dmalloc(&m->loss_acc, 2)); CK(dmalloc(&m->loss3, 4));
+    const float pw0[2] = {0.9f, 0.999f};
+    CK(cudaMemcpy(m->pw, pw0, 8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(m->loss_acc, 0, 16)); CK(cudaMemset(m->loss3, 0, 16));
+    CK(cudaHostAlloc((void**)&m->loss3_pinned, 16, cudaHostAllocDefault));
+    CK(dmalloc(&m->b_users, (size_t)m->cap)); CK(dmalloc(&m->b_pos, (size_t)m->cap)); CK(dmalloc(&m->b_neg, (size_t)m->cap));
+    CK(dmalloc(&m->b_time, (size_t)m->cap)); CK(dmalloc(&m->b_pp, (size_t)m->cap)); CK(dmalloc(&m->b_np, (size_t)m->cap));
+    CK(cudaDeviceSynchronize());
+    *out = m;
+    return PDA_OK;
+}
+
+void pda_destroy(pda_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->cfg.device);
+    cudaDeviceSynchronize();
+    for (int t = 0; t < 2; ++t) { cudaFree(m->W[t]); cudaFree(m->Mo[t]); cudaFree(m->Vo[t]); cudaFree(m->G[t]); }
+    cudaFree(m->pw); cudaFree(m->loss_acc); cudaFree(m->loss3); cudaFreeHost(m->loss3_pinned);
+    cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
+    cudaFree(m->pop_train);
+    cudaFree(m->b_users); cudaFree(m->b_pos); cudaFree(m->b_neg); cudaFree(m->b_time); cudaFree(m->b_pp); cudaFree(m->b_np);
+    if (m->stage_pinned) cudaFreeHost(m->stage_pinned);
+    if (m->ev_buf) cudaFree(m->ev_buf);
+    if (m->ev_pinned) cudaFreeHost(m->ev_pinned);
+    if (m->prof_ev) {
+        for (int k = 0; k < PDA_PROF_KINDS; ++k)
+            for (int i = 0; i < PDA_PROF_SLOTS; ++i) { cudaEventDestroy(m->prof_ev[k][i][0]); cudaEventDestroy(m->prof_ev[k][i][1]); }
+        free(m->prof_ev);
+    }
+    delete m;
+}
+
+int pda_profile_enable(pda_model* m, int on) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    if (on && !m->prof_ev) {
+        m->prof_ev = (cudaEvent_t(*)[PDA_PROF_SLOTS][2])calloc(PDA_PROF_KINDS, sizeof(cudaEvent_t) * PDA_PROF_SLOTS * 2);
+        if (!m->prof_ev) return fail(PDA_ERR_STATE, "out of host memory");
+        for (int k = 0; k < PDA_PROF_KINDS; ++k)
+            for (int i = 0; i < PDA_PROF_SLOTS; ++i) { CK(cudaEventCreate(&m->prof_ev[k][i][0])); CK(cudaEventCreate(&m->prof_ev[k][i][1])); }
+    }
+    m->prof_on = on;
+    for (int k = 0; k < PDA_PROF_KINDS; ++k) m->prof_n[k] = 0;
+    return PDA_OK;
+}
+
+int pda_profile_read(pda_model* m, double* ms_sum, int32_t* count) {
+    if (!m || !ms_sum || !count) return fail(PDA_ERR_ARG, "null argument");
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaDeviceSynchronize());
+    for (int k = 0; k < PDA_PROF_KINDS; ++k) {
+        ms_sum[k] = 0.0; count[k] = m->prof_ev ? m->prof_n[k] : 0;
+        for (int i = 0; i < count[k]; ++i) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, m->prof_ev[k][i][0], m->prof_ev[k][i][1]));
+            ms_sum[k] += ms;
+        }
+        m->prof_n[k] = 0;
+    }
+    return PDA_OK;
+}
+
+int pda_synchronize(pda_model* m) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaDeviceSynchronize());
+    return PDA_OK;
+}
+
+int pda_init_tables(pda_model* m, uint32_t seed) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    launch_xavier_init(m->W[0], m->nU, m->d, seed, 0u, 0);
+    launch_xavier_init(m->W[1], m->nI, m->d, seed, 1u, 0);
+    CK(cudaGetLastError());
+    const int64_t rows[2] = {m->nU, m->nI};
+    for (int t = 0; t < 2; ++t) {
+        size_t n = (size_t)rows[t] * m->d * 4;
+        CK(cudaMemsetAsync(m->Mo[t], 0, n)); CK(cudaMemsetAsync(m->Vo[t], 0, n)); CK(cudaMemsetAsync(m->G[t], 0, n));
+    }
+    const float pw0[2] = {0.9f, 0.999f};
+    CK(cudaMemcpy(m->pw, pw0, 8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(m->loss_acc, 0, 16));
+    CK(cudaDeviceSynchronize());
+    return PDA_OK;
+}
+
+static float* table_of(pda_model* m, int which, int64_t* rows) {
+    switch (which) {
+        case PDA_TABLE_USER: *rows = m->nU; return m->W[0];
+        case PDA_TABLE_ITEM: *rows = m->nI; return m->W[1];
+        case PDA_TABLE_USER_M: *rows = m->nU; return m->Mo[0];
+        case PDA_TABLE_USER_V: *rows = m->nU; return m->Vo[0];
+        case PDA_TABLE_ITEM_M: *rows = m->nI; return m->Mo[1];
+        case PDA_TABLE_ITEM_V: *rows = m->nI; return m->Vo[1];
+    }
+    return nullptr;
+}
+
+int pda_set_table(pda_model* m, int which, const float* src) {
+    if (!m || !src) return fail(PDA_ERR_ARG, "null argument");
+    int64_t rows; float* p = table_of(m, which, &rows);
+    if (!p) return fail(PDA_ERR_ARG, "unknown table %d", which);
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaMemcpy(p, src, (size_t)rows * m->d * 4, cudaMemcpyHostToDevice));
+    return PDA_OK;
+}
+int pda_get_table(pda_model* m, int which, float* dst) {
+    if (!m || !dst) return fail(PDA_ERR_ARG, "null argument");
+    int64_t rows; float* p = table_of(m, which, &rows);
+    if (!p) return fail(PDA_ERR_ARG, "unknown table %d", which);
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(dst, p, (size_t)rows * m->d * 4, cudaMemcpyDeviceToHost));
+    return PDA_OK;
+}
+void* pda_table_ptr(pda_model* m, int which) {
+    if (!m) return nullptr;
+    int64_t rows;
+    return table_of(m, which, &rows);
+}
+int pda_get_adam_powers(pda_model* m, float* out) {
+    if (!m || !out) return fail(PDA_ERR_ARG, "null argument");
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out, m->pw, 8, cudaMemcpyDeviceToHost));
+    return PDA_OK;
+}
+int pda_set_adam_powers(pda_model* m, const float* in) {
+    if (!m || !in) return fail(PDA_ERR_ARG, "null argument");
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaMemcpy(m->pw, in, 8, cudaMemcpyHostToDevice));
+    return PDA_OK;
+}
+
+int pda_set_train_csr(pda_model* m, const int64_t* indptr, const int32_t* items, const uint8_t* times, int64_t nnz,
+                      const int32_t* unique_times, int32_t n_times) {
+    if (!m || !indptr || (!items && nnz > 0)) return fail(PDA_ERR_ARG, "null argument");
+    if (indptr[0] != 0 || indptr[m->nU] != nnz) return fail(PDA_ERR_ARG, "indptr must span [0, nnz] over n_users rows");
+    CK(cudaSetDevice(m->cfg.device));
+    // rows must be sorted: the sampler's rejection test and the eval mask walk rely on it
+    int64_t n_act = 0;
+    for (int64_t u = 0; u < m->nU; ++u) {
+        if (indptr[u + 1] < indptr[u]) return fail(PDA_ERR_ARG, "indptr not monotone at row %lld", (long long)u);
+        if (indptr[u + 1] > indptr[u]) ++n_act;
+        for (int64_t q = indptr[u] + 1; q < indptr[u + 1]; ++q)
+            if (items[q] < items[q - 1]) return fail(PDA_ERR_ARG, "items of user %lld are not sorted", (long long)u);
+    }
+    for (int64_t q = 0; q < nnz; ++q)
+        if (items[q] < 0 || items[q] >= m->nI) return fail(PDA_ERR_ARG, "item id out of range at %lld", (long long)q);
+    cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
+    m->indptr = nullptr; m->items = nullptr; m->times = nullptr; m->active = nullptr; m->unique_times = nullptr;
+    CK(dmalloc(&m->indptr, (size_t)m->nU + 1));
+    CK(dmalloc(&m->items, (size_t)nnz));
+    CK(cudaMemcpy(m->indptr, indptr, ((size_t)m->nU + 1) * 8, cudaMemcpyHostToDevice));
+    if (nnz) CK(cudaMemcpy(m->items, items, (size_t)nnz * 4, cudaMemcpyHostToDevice));
+    if (times) {
+        CK(dmalloc(&m->times, (size_t)nnz));
+        if (nnz) CK(cudaMemcpy(m->times, times, (size_t)nnz, cudaMemcpyHostToDevice));
+    }
+    // users with training data, ascending (the reference samples from train_user_list.keys())
+    int32_t* act = (int32_t*)malloc(sizeof(int32_t) * (size_t)(n_act > 0 ? n_act : 1));
+    if (!act) return fail(PDA_ERR_STATE, "out of host memory");
+    int64_t k = 0;
+    for (int64_t u = 0; u < m->nU; ++u) if (indptr[u + 1] > indptr[u]) act[k++] = (int32_t)u;
+    CK(dmalloc(&m->active, (size_t)n_act));
+    if (n_act) CK(cudaMemcpy(m->active, act, (size_t)n_act * 4, cudaMemcpyHostToDevice));
+    free(act);
+    m->n_act = n_act; m->nnz = nnz;
+    m->n_times = 0;
+    if (unique_times && n_times > 0) {
+        CK(dmalloc(&m->unique_times, (size_t)n_times));
+        CK(cudaMemcpy(m->unique_times, unique_times, (size_t)n_times * 4, cudaMemcpyHostToDevice));
+        m->n_times = n_times;
+    }
+    return PDA_OK;
+}
+
+int pda_set_train_pop(pda_model* m, const float* pop, int32_t T_pop) {
+    if (!m || !pop || T_pop < 1) return fail(PDA_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(m->cfg.device));
+    cudaFree(m->pop_train); m->pop_train = nullptr;
+    CK(dmalloc(&m->pop_train, (size_t)m->nI * T_pop));
+    CK(cudaMemcpy(m->pop_train, pop, (size_t)m->nI * T_pop * 4, cudaMemcpyHostToDevice));
+    m->T_pop = T_pop;
+    return PDA_OK;
+}
+
+int pda_set_train_csr_device(pda_model* m, const int64_t* indptr_d, const int32_t* items_d, const uint8_t* times_d,
+                             int64_t nnz, const int32_t* active_d, int64_t n_act, const int32_t* unique_times, int32_t n_times) {
+    if (!m || !indptr_d || !items_d || !active_d || n_act < 1) return fail(PDA_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(m->cfg.device));
+    cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
+    m->indptr = nullptr; m->items = nullptr; m->times = nullptr; m->active = nullptr; m->unique_times = nullptr;
+    CK(dmalloc(&m->indptr, (size_t)m->nU + 1));
+    CK(dmalloc(&m->items, (size_t)nnz));
+    CK(dmalloc(&m->active, (size_t)n_act));
+    CK(cudaMemcpy(m->indptr, indptr_d, ((size_t)m->nU + 1) * 8, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(m->items, items_d, (size_t)nnz * 4, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(m->active, active_d, (size_t)n_act * 4, cudaMemcpyDeviceToDevice));
+    if (times_d) {
+        CK(dmalloc(&m->times, (size_t)nnz));
+        CK(cudaMemcpy(m->times, times_d, (size_t)nnz, cudaMemcpyDeviceToDevice));
+    }
+    m->n_act = n_act; m->nnz = nnz; m->n_times = 0;
+    if (unique_times && n_times > 0) {
+        CK(dmalloc(&m->unique_times, (size_t)n_times));
+        CK(cudaMemcpy(m->unique_times, unique_times, (size_t)n_times * 4, cudaMemcpyHostToDevice));
+        m->n_times = n_times;
+    }
+    return PDA_OK;
+}
+
+static int do_sample(pda_model* m, uint32_t seed, uint32_t epoch, uint32_t step, int64_t B, cudaStream_t st) {
+    if (!m->indptr) return fail(PDA_ERR_STATE, "pda_set_train_csr has not been called");
+    if (m->n_act < 1) return fail(PDA_ERR_STATE, "no user has training data");
+    if (B < 1 || B > m->cap) return fail(PDA_ERR_ARG, "B=%lld exceeds the batch capacity %lld", (long long)B, (long long)m->cap);
+    if (m->cfg.train_mode == PDA_TRAIN_S_CONDITION && !m->pop_train)
+        return fail(PDA_ERR_STATE, "train_mode s_condition needs pda_set_train_pop");
+    if (m->pop_train && m->T_pop > 1 && !m->times) return fail(PDA_ERR_STATE, "time-dependent popularity needs interaction times");
+    SamplerArgs a;
+    memset(&a, 0, sizeof(a));
+    a.seed = seed; a.epoch = epoch; a.step = step; a.B = B;
+    a.active_users = m->active; a.n_act = m->n_act;
+    a.indptr = m->indptr; a.items = m->items; a.times = m->times; a.n_items = (int32_t)m->nI;
+    a.unique_times = m->unique_times; a.n_times = m->n_times;
+    a.pop_train = m->cfg.train_mode == PDA_TRAIN_S_CONDITION ? m->pop_train : nullptr; a.T_pop = m->T_pop;
+    a.users_out = m->b_users; a.pos_out = m->b_pos; a.neg_out = m->b_neg; a.time_out = m->b_time;
+    a.pos_pop_out = m->b_pp; a.neg_pop_out = m->b_np;
+    { ProfScope ps(m, PDA_PROF_SAMPLER, st); launch_sampler(a, st); }
+    m->batch_uniq = B <= m->n_act;
+    return PDA_OK;
+}
+
+int pda_sample_batch(pda_model* m, uint32_t seed, uint32_t epoch, uint32_t step, int64_t B, void* stream) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    int rc = do_sample(m, seed, epoch, step, B, (cudaStream_t)stream);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+int pda_get_batch(pda_model* m, int64_t B, int32_t* users, int32_t* pos, int32_t* neg, int32_t* time, float* pp,
+                  float* np_) {
+    if (!m || B < 1 || B > m->cap) return fail(PDA_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaDeviceSynchronize());
+    if (users) CK(cudaMemcpy(users, m->b_users, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    if (pos) CK(cudaMemcpy(pos, m->b_pos, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    if (neg) CK(cudaMemcpy(neg, m->b_neg, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    if (time) CK(cudaMemcpy(time, m->b_time, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    if (pp) CK(cudaMemcpy(pp, m->b_pp, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    if (np_) CK(cudaMemcpy(np_, m->b_np, (size_t)B * 4, cudaMemcpyDeviceToHost));
+    return PDA_OK;
+}
+
+// gather -> loss -> gradient scatter: ONE kernel (gradients land in the table-shaped accumulators G)
+static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
+                           const float* np_, int64_t B, int uniq, cudaStream_t st) {
+    StepArgs s;
+    memset(&s, 0, sizeof(s));
+    s.U = m->W[0]; s.I = m->W[1]; s.GU = m->G[0]; s.GI = m->G[1];
+    s.users = users; s.pos = pos; s.neg = neg; s.pos_pop = pp; s.neg_pop = np_;
+    s.B = B; s.d = m->d;
+    s.lb = (float)((double)m->cfg.regs / (double)m->cfg.batch_size);
+    m->last_B = m->global_batch > 0 ? m->global_batch : B;
+    s.invB = 1.0f / (float)m->last_B;
+    s.loss_acc = m->loss_acc;
+    s.pop_mode = m->cfg.train_mode == PDA_TRAIN_S_CONDITION;
+    s.uniq_users = uniq;
+    ProfScope ps(m, PDA_PROF_STEP, st);
+    if (launch_bpr_step(s, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
+    return PDA_OK;
+}
+
+// TF1 Adam sweep over both tables (one kernel) + loss / beta-power bookkeeping
+static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st) {
+    if (apply_adam) {
+        AdamArgs a;
+        for (int t = 0; t < 2; ++t) { a.W[t] = m->W[t]; a.m[t] = m->Mo[t]; a.v[t] = m->Vo[t]; a.G[t] = m->G[t]; }
+        a.n4[0] = m->nU * m->d / 4; a.n4[1] = m->nI * m->d / 4;
+        a.pw = m->pw; a.lr = m->cfg.lr;
+        ProfScope ps(m, PDA_PROF_ADAM, st);
+        launch_adam_dense(a, st);
+    }
+    launch_finish_step(m->loss_acc, m->loss3, m->pw, m->last_B, m->cfg.regs, m->cfg.batch_size, apply_adam ? 1 : 0, st);
+    return PDA_OK;
+}
+
+static int enqueue_step(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
+                        const float* np_, int64_t B, int uniq, bool apply_adam, cudaStream_t st) {
+    int rc = enqueue_fwd_bwd(m, users, pos, neg, pp, np_, B, uniq, st);
+    if (rc) return rc;
+    return enqueue_adam(m, apply_adam, st);
+}
+
+int pda_set_global_batch(pda_model* m, int64_t global_batch) {
+    if (!m || global_batch < 0) return fail(PDA_ERR_ARG, "bad argument");
+    m->global_batch = global_batch;
+    return PDA_OK;
+}
+
+void* pda_grad_ptr(pda_model* m, int which) {
+    if (!m) return nullptr;
+    if (which == PDA_TABLE_USER) return m->G[0];
+    if (which == PDA_TABLE_ITEM) return m->G[1];
+    return nullptr;
+}
+
+void* pda_loss_acc_ptr(pda_model* m) { return m ? m->loss_acc : nullptr; }
+
+int pda_forward_backward_device(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
+                                const float* pp, const float* np_, int64_t B, void* stream) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    int uniq = 0;
+    if (!users) {
+        if (B < 1 || B > m->cap) return fail(PDA_ERR_ARG, "B exceeds the batch capacity");
+        users = m->b_users; pos = m->b_pos; neg = m->b_neg; pp = m->b_pp; np_ = m->b_np;
+        uniq = m->batch_uniq;
+    }
+    if (!pos || !neg) return fail(PDA_ERR_ARG, "null index pointer");
+    if (m->cfg.train_mode == PDA_TRAIN_S_CONDITION && (!pp || !np_)) return fail(PDA_ERR_ARG, "s_condition needs pos_pop/neg_pop");
+    int rc = enqueue_fwd_bwd(m, users, pos, neg, pp, np_, B, uniq, (cudaStream_t)stream);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+int pda_adam_apply(pda_model* m, void* stream) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    int rc = enqueue_adam(m, true, (cudaStream_t)stream);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
+                         const float* np_, int64_t B, void* stream);
+
+int pda_train_step_device(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
+                          const float* pp, const float* np_, int64_t B, void* stream) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    int uniq = 0;
+    if (!users) {   // internal batch from the device sampler: users are distinct iff B <= #active users
+        if (B < 1 || B > m->cap) return fail(PDA_ERR_ARG, "B exceeds the batch capacity");
+        users = m->b_users; pos = m->b_pos; neg = m->b_neg; pp = m->b_pp; np_ = m->b_np;
+        uniq = m->batch_uniq;
+    }
+    if (!pos || !neg) return fail(PDA_ERR_ARG, "null index pointer");
+    if (m->cfg.train_mode == PDA_TRAIN_S_CONDITION && (!pp || !np_)) return fail(PDA_ERR_ARG, "s_condition needs pos_pop/neg_pop");
+    int rc = enqueue_step(m, users, pos, neg, pp, np_, B, uniq, true, (cudaStream_t)stream);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+static int stage_batch(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
+                       const float* np_, int64_t B, cudaStream_t st) {
+    if (B < 1 || B > m->cap) return fail(PDA_ERR_ARG, "B=%lld exceeds the batch capacity %lld", (long long)B, (long long)m->cap);
+    const bool pop = m->cfg.train_mode == PDA_TRAIN_S_CONDITION;
+    if (!users || !pos || !neg || (pop && (!pp || !np_))) return fail(PDA_ERR_ARG, "null batch pointer");
+    // one pinned staging block, one DMA per array
+    m->batch_uniq = 0;
+    const size_t nb = (size_t)B * 4;
+    // caller buffers already pinned (pda_host_alloc / cudaHostAlloc): DMA straight from them
+    cudaPointerAttributes at;
+    bool pinned = cudaPointerGetAttributes(&at, users) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    if (!pinned) cudaGetLastError();
+    const char *su = (const char*)users, *sp = (const char*)pos, *sn = (const char*)neg, *spp = (const char*)pp,
+               *snp = (const char*)np_;
+    if (!pinned) {   // pageable memory: one pinned staging block, then one DMA per array
+        CK(ensure_pinned(&m->stage_pinned, &m->stage_bytes, nb * 5));
+        char* s = (char*)m->stage_pinned;
+        memcpy(s, users, nb); memcpy(s + nb, pos, nb); memcpy(s + 2 * nb, neg, nb);
+        su = s; sp = s + nb; sn = s + 2 * nb;
+        if (pop) { memcpy(s + 3 * nb, pp, nb); memcpy(s + 4 * nb, np_, nb); spp = s + 3 * nb; snp = s + 4 * nb; }
+    }
+    CK(cudaMemcpyAsync(m->b_users, su, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m->b_pos, sp, nb, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(m->b_neg, sn, nb, cudaMemcpyHostToDevice, st));
+    if (pop) {
+        CK(cudaMemcpyAsync(m->b_pp, spp, nb, cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(m->b_np, snp, nb, cudaMemcpyHostToDevice, st));
+    }
+    return PDA_OK;
+}
+
+int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
+                         const float* np_, int64_t B, void* stream) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    return stage_batch(m, users, pos, neg, pp, np_, B, (cudaStream_t)stream);
+}
+
+int pda_train_step_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
+                        const float* pp, const float* np_, int64_t B, float* loss3_out) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    int rc = stage_batch(m, users, pos, neg, pp, np_, B, 0);
+    if (rc) return rc;
+    rc = enqueue_step(m, m->b_users, m->b_pos, m->b_neg, m->b_pp, m->b_np, B, 0, true, 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(m->loss3_pinned, m->loss3, 12, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    CK(cudaGetLastError());
+    if (loss3_out) memcpy(loss3_out, m->loss3_pinned, 12);
+    return PDA_OK;
+}
+
+int pda_train_steps_sampled(pda_model* m, uint32_t seed, uint32_t epoch, uint32_t step0, int32_t n_steps, int64_t B,
+                            void* stream) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int32_t k = 0; k < n_steps; ++k) {
+        int rc = do_sample(m, seed, epoch, step0 + (uint32_t)k, B, st);
+        if (rc) return rc;
+        rc = enqueue_step(m, m->b_users, m->b_pos, m->b_neg, m->b_pp, m->b_np, B, m->batch_uniq, true, st);
+        if (rc) return rc;
+    }
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+int pda_read_loss(pda_model* m, float* loss3_out, void* stream) {
+    if (!m || !loss3_out) return fail(PDA_ERR_ARG, "null argument");
+    CK(cudaSetDevice(m->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    CK(cudaMemcpyAsync(m->loss3_pinned, m->loss3, 12, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(loss3_out, m->loss3_pinned, 12);
+    return PDA_OK;
+}
+
+int pda_gradients_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
+                       const float* np_, int64_t B, float* gU_out, float* gI_out, float* loss3_out) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    int rc = stage_batch(m, users, pos, neg, pp, np_, B, 0);
+    if (rc) return rc;
+    rc = enqueue_step(m, m->b_users, m->b_pos, m->b_neg, m->b_pp, m->b_np, B, 0, false, 0);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(0));
+    CK(cudaGetLastError());
+    if (gU_out) CK(cudaMemcpy(gU_out, m->G[0], (size_t)m->nU * m->d * 4, cudaMemcpyDeviceToHost));
+    if (gI_out) CK(cudaMemcpy(gI_out, m->G[1], (size_t)m->nI * m->d * 4, cudaMemcpyDeviceToHost));
+    if (loss3_out) CK(cudaMemcpy(loss3_out, m->loss3, 12, cudaMemcpyDeviceToHost));
+    CK(cudaMemset(m->G[0], 0, (size_t)m->nU * m->d * 4));
+    CK(cudaMemset(m->G[1], 0, (size_t)m->nI * m->d * 4));
+    return PDA_OK;
+}
+
+// ---- recommendation ----
+static int do_recommend(pda_model* m, const EvalArgs& a, int backend, cudaStream_t st) {
+    if (backend == PDA_EVAL_TENSOR) return fail(PDA_ERR_ARG, "tensor-core eval back end is not built into this library yet");
+    ProfScope ps(m, PDA_PROF_EVAL, st);
+    if (launch_recommend_exact(a, st)) return fail(PDA_ERR_ARG, "bad eval arguments (K in [1,128], M >= 1)");
+    return PDA_OK;
+}
+
+int pda_recommend_device(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop,
+                         const float* col_bias, int use_mask, int K, int backend, int32_t* ids_out, float* scores_out,
+                         void* stream) {
+    if (!m || !users || !ids_out) return fail(PDA_ERR_ARG, "null argument");
+    if (rec_type == PDA_REC_WITH_POP && !pop) return fail(PDA_ERR_ARG, "rec_type with_pop needs pop");
+    if (use_mask && !m->indptr) return fail(PDA_ERR_STATE, "mask requested but pda_set_train_csr was not called");
+    CK(cudaSetDevice(m->cfg.device));
+    EvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.U = m->W[0]; a.I = m->W[1]; a.N = m->nI; a.d = m->d; a.users = users; a.M = M;
+    a.mode = rec_type == PDA_REC_WITH_POP ? 1 : 0;
+    a.pop = pop; a.col_bias = col_bias;
+    a.mask_indptr = use_mask ? m->indptr : nullptr; a.mask_items = use_mask ? m->items : nullptr;
+    a.K = K; a.ids_out = ids_out; a.scores_out = scores_out;
+    int rc = do_recommend(m, a, backend, (cudaStream_t)stream);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+int pda_recommend_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop,
+                       const float* col_bias, int use_mask, int K, int backend, int32_t* ids_out, float* scores_out) {
+    if (!m || !users || !ids_out || M < 1 || K < 1) return fail(PDA_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(m->cfg.device));
+    const size_t nu = ((size_t)M * 4 + 255) / 256 * 256, nv = ((size_t)m->nI * 4 + 255) / 256 * 256;
+    const size_t nk = ((size_t)M * K * 4 + 255) / 256 * 256;
+    CK(ensure_dev(&m->ev_buf, &m->ev_bytes, nu + 2 * nv + 2 * nk));
+    char* b = (char*)m->ev_buf;
+    int32_t* d_users = (int32_t*)b; float* d_pop = (float*)(b + nu); float* d_bias = (float*)(b + nu + nv);
+    int32_t* d_ids = (int32_t*)(b + nu + 2 * nv); float* d_sc = (float*)(b + nu + 2 * nv + nk);
+    CK(cudaMemcpyAsync(d_users, users, (size_t)M * 4, cudaMemcpyHostToDevice, 0));
+    if (pop) CK(cudaMemcpyAsync(d_pop, pop, (size_t)m->nI * 4, cudaMemcpyHostToDevice, 0));
+    if (col_bias) CK(cudaMemcpyAsync(d_bias, col_bias, (size_t)m->nI * 4, cudaMemcpyHostToDevice, 0));
+    int rc = pda_recommend_device(m, d_users, M, rec_type, pop ? d_pop : nullptr, col_bias ? d_bias : nullptr, use_mask, K,
+                                  backend, d_ids, scores_out ? d_sc : nullptr, 0);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(ids_out, d_ids, (size_t)M * K * 4, cudaMemcpyDeviceToHost, 0));
+    if (scores_out) CK(cudaMemcpyAsync(scores_out, d_sc, (size_t)M * K * 4, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+int pda_scores_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop, float* out) {
+    if (!m || !users || !out || M < 1) return fail(PDA_ERR_ARG, "bad argument");
+    if (rec_type == PDA_REC_WITH_POP && !pop) return fail(PDA_ERR_ARG, "rec_type with_pop needs pop");
+    CK(cudaSetDevice(m->cfg.device));
+    const size_t nu = ((size_t)M * 4 + 255) / 256 * 256, nv = ((size_t)m->nI * 4 + 255) / 256 * 256;
+    const size_t nd = (size_t)M * m->nI * 4;
+    CK(ensure_dev(&m->ev_buf, &m->ev_bytes, nu + nv + 256 + nd));
+    char* b = (char*)m->ev_buf;
+    int32_t* d_users = (int32_t*)b; float* d_pop = (float*)(b + nu); int32_t* d_ids = (int32_t*)(b + nu + nv);
+    float* d_dense = (float*)(b + nu + nv + 256);
+    CK(cudaMemcpyAsync(d_users, users, (size_t)M * 4, cudaMemcpyHostToDevice, 0));
+    if (pop) CK(cudaMemcpyAsync(d_pop, pop, (size_t)m->nI * 4, cudaMemcpyHostToDevice, 0));
+    EvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.U = m->W[0]; a.I = m->W[1]; a.N = m->nI; a.d = m->d; a.users = d_users; a.M = M;
+    a.mode = rec_type == PDA_REC_WITH_POP ? 1 : 0; a.pop = pop ? d_pop : nullptr;
+    a.K = 1; a.ids_out = nullptr; a.scores_out = nullptr; a.dense_out = d_dense;
+    (void)d_ids;
+    if (launch_recommend_exact(a, 0)) return fail(PDA_ERR_ARG, "bad eval arguments");
+    CK(cudaMemcpyAsync(out, d_dense, nd, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+int pda_metrics_host(pda_model* m, const int32_t* ids, int64_t M, int Kkeep, const int32_t* eval_users,
+                     const int64_t* truth_indptr, const int32_t* truth_items, int64_t n_truth_rows, const int32_t* Ks,
+                     int nK, double* out) {
+    if (!m || !ids || !eval_users || !truth_indptr || !Ks || !out || M < 1 || nK < 1 || nK > 16)
+        return fail(PDA_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(m->cfg.device));
+    const int64_t nnz = truth_indptr[n_truth_rows];
+    auto al = [](size_t x) { return (x + 255) / 256 * 256; };
+    const size_t o_ids = 0, o_users = o_ids + al((size_t)M * Kkeep * 4), o_ptr = o_users + al((size_t)M * 4);
+    const size_t o_items = o_ptr + al(((size_t)n_truth_rows + 1) * 8), o_ks = o_items + al((size_t)(nnz > 0 ? nnz : 1) * 4);
+    const size_t o_out = o_ks + al((size_t)nK * 4), total = o_out + al((size_t)4 * nK * 8);
+    CK(ensure_dev(&m->ev_buf, &m->ev_bytes, total));
+    char* b = (char*)m->ev_buf;
+    CK(cudaMemcpyAsync(b + o_ids, ids, (size_t)M * Kkeep * 4, cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(b + o_users, eval_users, (size_t)M * 4, cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(b + o_ptr, truth_indptr, ((size_t)n_truth_rows + 1) * 8, cudaMemcpyHostToDevice, 0));
+    if (nnz) CK(cudaMemcpyAsync(b + o_items, truth_items, (size_t)nnz * 4, cudaMemcpyHostToDevice, 0));
+    CK(cudaMemcpyAsync(b + o_ks, Ks, (size_t)nK * 4, cudaMemcpyHostToDevice, 0));
+    CK(cudaMemsetAsync(b + o_out, 0, (size_t)4 * nK * 8, 0));
+    launch_metrics((const int32_t*)(b + o_ids), M, Kkeep, (const int32_t*)(b + o_users), (const int64_t*)(b + o_ptr),
+                   (const int32_t*)(b + o_items), (const int32_t*)(b + o_ks), nK, (double*)(b + o_out), 0);
+    CK(cudaMemcpyAsync(out, b + o_out, (size_t)4 * nK * 8, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,62 @@
+// Internal launch interface between the C-ABI layer (pda_capi.cu) and the kernel files.
+#pragma once
+#include "pda_common.cuh"
+
+namespace pda {
+
+struct SamplerArgs {
+    uint32_t seed, epoch, step;
+    int64_t B;
+    const int32_t* active_users; int64_t n_act;
+    const int64_t* indptr; const int32_t* items; const uint8_t* times;
+    int32_t n_items;
+    const int32_t* unique_times; int32_t n_times;
+    const float* pop_train; int32_t T_pop;
+    int32_t *users_out, *pos_out, *neg_out, *time_out;
+    float *pos_pop_out, *neg_pop_out;
+    uint32_t keys[6]; int half_bits;   // filled by launch_sampler
+};
+
+struct StepArgs {
+    const float* U; const float* I;
+    float* GU; float* GI;
+    const int32_t *users, *pos, *neg;
+    const float *pos_pop, *neg_pop;
+    int64_t B; int d;
+    float lb;     // regs / batch_size
+    float invB;   // 1 / B
+    double* loss_acc;
+    int pop_mode;     // 0: create_bpr_loss, 1: create_bpr_loss_with_pop_global
+    int uniq_users;   // users distinct within the batch -> plain stores for the user rows
+};
+
+struct AdamArgs {
+    float* W[2]; float* m[2]; float* v[2]; float* G[2];
+    int64_t n4[2];       // float4 count of each table
+    const float* pw;     // {beta1_power, beta2_power}
+    float lr;
+};
+
+struct EvalArgs {
+    const float* U; const float* I; int64_t N; int d;
+    const int32_t* users; int64_t M;
+    int mode;                 // 0: y = s (+ col_bias), 1: y = (elu(s)+1) * pop
+    const float* pop; const float* col_bias;
+    const int64_t* mask_indptr; const int32_t* mask_items;   // CSR over global user ids, rows sorted
+    int K;
+    int32_t* ids_out; float* scores_out;    // [M,K]
+    float* dense_out;                       // optional [M,N] transformed scores (unmasked)
+};
+
+void launch_xavier_init(float* W, int64_t rows, int cols, uint32_t seed, uint32_t table_id, cudaStream_t st);
+void sampler_keys(uint32_t seed, uint32_t epoch, uint32_t step, uint32_t* keys);
+void launch_sampler(SamplerArgs a, cudaStream_t st);
+int launch_bpr_step(const StepArgs& a, cudaStream_t st);
+void launch_adam_dense(const AdamArgs& a, cudaStream_t st);
+void launch_finish_step(double* loss_acc, float* loss3, float* pw, int64_t B, float regs, int batch_size,
+                        int advance_powers, cudaStream_t st);
+int launch_recommend_exact(const EvalArgs& a, cudaStream_t st);
+void launch_metrics(const int32_t* ids, int64_t M, int Kkeep, const int32_t* eval_users, const int64_t* truth_indptr,
+                    const int32_t* truth_items, const int32_t* Ks, int nK, double* out, cudaStream_t st);
+
+}  // namespace pda

@@ -1,0 +1,334 @@
+// Training-side kernels of the PDA hot path: Xavier init, device sampler, the fused BPR step
+// and the TF1-semantics Adam sweep.  Reference call sites (paths under the upstream repo):
+//   init      MF/model_api.py:86-99
+//   sampler   MF/train_new_api.py:260-288 (BPRMF), :366-412 (PD), :415-456 (BPR(t)-pop)
+//   step      MF/model_api.py:51-53 (gather), :102-121 (PD loss), :123-134 (BPRMF loss)
+//   optimizer MF/model_api.py:83,471 -> tf.train.AdamOptimizer on IndexedSlices (dense sweep)
+#include "pda_kernels.h"
+
+namespace pda {
+
+// ------------------------------------------------------------------------------------------
+// a1. Xavier-uniform init: element e = 4q + w takes word w of Philox(ctr=(q_lo,q_hi,table,0)).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) xavier_init_kernel(float* __restrict__ W, int64_t n, float a, uint32_t seed,
+                                                          uint32_t table_id) {
+    int64_t nq = (n + 3) / 4;
+    for (int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; q < nq; q += (int64_t)gridDim.x * blockDim.x) {
+        u32x4 r = philox4x32((uint32_t)q, (uint32_t)((uint64_t)q >> 32), table_id, 0u, seed, TAG_INIT);
+        float x[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            float u = fmul((float)(r.w[w] >> 8), 5.9604644775390625e-8f);
+            x[w] = fmul(fsub(fmul(u, 2.0f), 1.0f), a);
+        }
+        int64_t e = 4 * q;
+        if (e + 3 < n) {
+            *reinterpret_cast<float4*>(W + e) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+            for (int w = 0; w < 4 && e + w < n; ++w) W[e + w] = x[w];
+        }
+    }
+}
+
+void launch_xavier_init(float* W, int64_t rows, int cols, uint32_t seed, uint32_t table_id, cudaStream_t st) {
+    int64_t n = rows * cols;
+    float a = (float)sqrt(6.0 / (double)(rows + cols));
+    int64_t nq = (n + 3) / 4;
+    int blocks = (int)((nq + 255) / 256 < 148 * 16 ? (nq + 255) / 256 : 148 * 16);
+    if (blocks < 1) blocks = 1;
+    xavier_init_kernel<<<blocks, 256, 0, st>>>(W, n, a, seed, table_id);
+}
+
+// ------------------------------------------------------------------------------------------
+// a8. device sampler.  One thread per batch slot; word stream of slot i:
+// Philox(ctr=(i, call, step, epoch), key=(seed, TAG_SAMPLE)), call = 0,1,...; word 0 -> pos
+// (or the time slot of a user with an empty list), words 1.. -> negative candidates, each
+// rejected by binary search in the user's sorted train row.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool row_contains(const int32_t* __restrict__ items, int64_t lo, int64_t hi, int32_t c) {
+    int64_t end = hi;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (__ldg(items + mid) < c) lo = mid + 1; else hi = mid;
+    }
+    return lo < end && __ldg(items + lo) == c;
+}
+
+__global__ void __launch_bounds__(128) sample_kernel(SamplerArgs a) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < a.B; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t u;
+        if (a.B <= a.n_act) {
+            uint32_t y = feistel_once((uint32_t)i, a.half_bits, a.keys);
+            while (y >= (uint32_t)a.n_act) y = feistel_once(y, a.half_bits, a.keys);
+            u = __ldg(a.active_users + y);
+        } else {
+            u32x4 r = philox4x32((uint32_t)i, 0u, a.step, a.epoch, a.seed, TAG_USER);
+            u = __ldg(a.active_users + mulhi32(r.w[0], (uint32_t)a.n_act));
+        }
+        u32x4 w = philox4x32((uint32_t)i, 0u, a.step, a.epoch, a.seed, TAG_SAMPLE);
+        int64_t lo = __ldg(a.indptr + u), hi = __ldg(a.indptr + u + 1);
+        uint32_t deg = (uint32_t)(hi - lo);
+        int32_t pos, t;
+        if (deg > 0) {
+            int64_t at = lo + mulhi32(w.w[0], deg);
+            pos = __ldg(a.items + at);
+            t = a.times ? (int32_t)__ldg(a.times + at) : 0;
+        } else {
+            pos = 0;
+            t = a.n_times > 0 ? __ldg(a.unique_times + mulhi32(w.w[0], (uint32_t)a.n_times)) : 0;
+        }
+        uint32_t call = 0;
+        int32_t neg;
+        for (uint32_t k = 1;; ++k) {
+            if ((k & 3u) == 0) { ++call; w = philox4x32((uint32_t)i, call, a.step, a.epoch, a.seed, TAG_SAMPLE); }
+            int32_t c = (int32_t)mulhi32(w.w[k & 3u], (uint32_t)a.n_items);
+            if (!row_contains(a.items, lo, hi, c)) { neg = c; break; }
+        }
+        a.users_out[i] = u; a.pos_out[i] = pos; a.neg_out[i] = neg;
+        if (a.time_out) a.time_out[i] = t;
+        if (a.pop_train) {
+            int32_t tt = a.T_pop == 1 ? 0 : t;
+            a.pos_pop_out[i] = __ldg(a.pop_train + (int64_t)pos * a.T_pop + tt);
+            a.neg_pop_out[i] = __ldg(a.pop_train + (int64_t)neg * a.T_pop + tt);
+        }
+    }
+}
+
+void sampler_keys(uint32_t seed, uint32_t epoch, uint32_t step, uint32_t* keys) {
+    u32x4 ka = philox4x32(0u, 0u, step, epoch, seed, TAG_PERM), kb = philox4x32(1u, 0u, step, epoch, seed, TAG_PERM);
+    keys[0] = ka.w[0]; keys[1] = ka.w[1]; keys[2] = ka.w[2]; keys[3] = ka.w[3];
+    keys[4] = kb.w[0]; keys[5] = kb.w[1];
+}
+
+void launch_sampler(SamplerArgs a, cudaStream_t st) {
+    sampler_keys(a.seed, a.epoch, a.step, a.keys);
+    a.half_bits = feistel_half_bits((uint32_t)a.n_act);
+    int64_t blocks = (a.B + 127) / 128;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    sample_kernel<<<(int)blocks, 128, 0, st>>>(a);
+}
+
+// ------------------------------------------------------------------------------------------
+// a2-a4 + gradient scatter: the fused BPR step.
+//
+// A group of G lanes owns one triple: each lane holds C float4 chunks of u, p, n (chunk c of
+// lane l covers elements 4(l + G c) ..+3), loaded with 128-bit coalesced LDGs (a d=128 row is
+// one 512 B warp request; at d=64 a warp carries two triples).  The two dot products are a
+// per-lane sequential sum followed by an xor-butterfly over the G lanes (the order the oracle's
+// dot_tree restates); every lane then evaluates the scalar chain redundantly (no divergence,
+// no broadcast), forms its slice of the three gradient rows from the registers that still
+// hold u, p, n and reduces them into the table-shaped gradient accumulators GU / GI with
+// 128-bit red.global.add (users are distinct within a batch when B <= #active users, so the
+// user row takes a plain store then).  Loss terms: per-lane partials -> warp shuffle ->
+// one fp64 atomic pair per warp.
+// ------------------------------------------------------------------------------------------
+template <int G, int C, bool POP, bool UNIQ>
+__global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
+    constexpr int GPW = 32 / G;  // triples per warp per iteration
+    const int lane = threadIdx.x & 31;
+    const int gl = lane % G;       // lane within the group
+    const int gw = lane / G;       // group within the warp
+    const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int q = a.d >> 2;  // float4 chunks per row
+
+    double mf_acc = 0.0, sq_acc = 0.0;
+
+    for (int64_t base = warp_global * GPW; base < a.B; base += n_warps * GPW) {
+        const int64_t i = base + gw;
+        const bool valid = i < a.B;
+        int32_t iu = 0, ip = 0, in = 0;
+        float pp = 1.0f, pn = 1.0f;
+        if (valid) {
+            iu = __ldg(a.users + i); ip = __ldg(a.pos + i); in = __ldg(a.neg + i);
+            if (POP) { pp = __ldg(a.pos_pop + i); pn = __ldg(a.neg_pop + i); }
+        }
+        const float* ur = a.U + (int64_t)iu * a.d;
+        const float* pr = a.I + (int64_t)ip * a.d;
+        const float* nr = a.I + (int64_t)in * a.d;
+        float4 u[C], p[C], n[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int ch = gl + G * c;
+            if (valid && ch < q) {
+                u[c] = ldg_f4(ur + 4 * ch); p[c] = ldg_f4(pr + 4 * ch); n[c] = ldg_f4(nr + 4 * ch);
+            } else {
+                u[c] = p[c] = n[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        float sp = 0.0f, sn = 0.0f, sq = 0.0f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            sp = fadd(sp, fmul(u[c].x, p[c].x)); sp = fadd(sp, fmul(u[c].y, p[c].y));
+            sp = fadd(sp, fmul(u[c].z, p[c].z)); sp = fadd(sp, fmul(u[c].w, p[c].w));
+            sn = fadd(sn, fmul(u[c].x, n[c].x)); sn = fadd(sn, fmul(u[c].y, n[c].y));
+            sn = fadd(sn, fmul(u[c].z, n[c].z)); sn = fadd(sn, fmul(u[c].w, n[c].w));
+            sq += u[c].x * u[c].x + u[c].y * u[c].y + u[c].z * u[c].z + u[c].w * u[c].w;
+            sq += p[c].x * p[c].x + p[c].y * p[c].y + p[c].z * p[c].z + p[c].w * p[c].w;
+            sq += n[c].x * n[c].x + n[c].y * n[c].y + n[c].z * n[c].z + n[c].w * n[c].w;
+        }
+#pragma unroll
+        for (int off = G / 2; off >= 1; off >>= 1) {
+            sp = fadd(sp, __shfl_xor_sync(0xffffffffu, sp, off));
+            sn = fadd(sn, __shfl_xor_sync(0xffffffffu, sn, off));
+        }
+        // scalar chain (model_api.py:107-114 / 124-126)
+        float x, dp, dn;
+        if (POP) {
+            x = fsub(fmul(elu_p1(sp), pp), fmul(elu_p1(sn), pn));
+            dp = fmul(elu_p1_grad(sp), pp);
+            dn = fmul(elu_p1_grad(sn), pn);
+        } else {
+            x = fsub(sp, sn); dp = 1.0f; dn = 1.0f;
+        }
+        const float sig = fdiv(1.0f, fadd(1.0f, spec_expf(-x)));
+        const float sige = fadd(sig, 1e-10f);
+        const float g = fdiv(fmul(sig, fsub(1.0f, sig)), sige);
+        const float cp = fmul(fmul(-g, dp), a.invB);
+        const float cn = fmul(fmul(g, dn), a.invB);
+        if (valid) {
+            sq_acc += (double)sq;
+            if (gl == 0) mf_acc += (double)logf(sige);
+            float* gu = a.GU + (int64_t)iu * a.d;
+            float* gp = a.GI + (int64_t)ip * a.d;
+            float* gn = a.GI + (int64_t)in * a.d;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int ch = gl + G * c;
+                if (ch < q) {
+                    float4 du, dpv, dnv;
+                    du.x = fadd(fadd(fmul(cp, p[c].x), fmul(cn, n[c].x)), fmul(a.lb, u[c].x));
+                    du.y = fadd(fadd(fmul(cp, p[c].y), fmul(cn, n[c].y)), fmul(a.lb, u[c].y));
+                    du.z = fadd(fadd(fmul(cp, p[c].z), fmul(cn, n[c].z)), fmul(a.lb, u[c].z));
+                    du.w = fadd(fadd(fmul(cp, p[c].w), fmul(cn, n[c].w)), fmul(a.lb, u[c].w));
+                    dpv.x = fadd(fmul(cp, u[c].x), fmul(a.lb, p[c].x));
+                    dpv.y = fadd(fmul(cp, u[c].y), fmul(a.lb, p[c].y));
+                    dpv.z = fadd(fmul(cp, u[c].z), fmul(a.lb, p[c].z));
+                    dpv.w = fadd(fmul(cp, u[c].w), fmul(a.lb, p[c].w));
+                    dnv.x = fadd(fmul(cn, u[c].x), fmul(a.lb, n[c].x));
+                    dnv.y = fadd(fmul(cn, u[c].y), fmul(a.lb, n[c].y));
+                    dnv.z = fadd(fmul(cn, u[c].z), fmul(a.lb, n[c].z));
+                    dnv.w = fadd(fmul(cn, u[c].w), fmul(a.lb, n[c].w));
+                    if (UNIQ) *reinterpret_cast<float4*>(gu + 4 * ch) = du;
+                    else red_add_f4(gu + 4 * ch, du);
+                    red_add_f4(gp + 4 * ch, dpv);
+                    red_add_f4(gn + 4 * ch, dnv);
+                }
+            }
+        }
+    }
+    // loss partials: warp reduce, one fp64 atomic pair per warp
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        mf_acc += __shfl_xor_sync(0xffffffffu, mf_acc, off);
+        sq_acc += __shfl_xor_sync(0xffffffffu, sq_acc, off);
+    }
+    if (lane == 0) {
+        atomicAdd(a.loss_acc + 0, mf_acc);
+        atomicAdd(a.loss_acc + 1, sq_acc);
+    }
+}
+
+template <int G, int C>
+static void launch_step_gc(const StepArgs& a, int grid, cudaStream_t st) {
+    if (a.pop_mode) {
+        if (a.uniq_users) bpr_step_kernel<G, C, true, true><<<grid, 256, 0, st>>>(a);
+        else bpr_step_kernel<G, C, true, false><<<grid, 256, 0, st>>>(a);
+    } else {
+        if (a.uniq_users) bpr_step_kernel<G, C, false, true><<<grid, 256, 0, st>>>(a);
+        else bpr_step_kernel<G, C, false, false><<<grid, 256, 0, st>>>(a);
+    }
+}
+
+int launch_bpr_step(const StepArgs& a, cudaStream_t st) {
+    if (a.d % 4 != 0 || a.d < 4 || a.d > 512) return 1;
+    const int q = a.d / 4;
+    int G = 1;
+    while (G < q && G < 32) G *= 2;
+    const int C = (q + G - 1) / G;
+    // grid: enough warps to cover the batch once, capped at 8 resident CTAs x 148 SMs
+    int64_t warps_needed = (a.B + (32 / G) - 1) / (32 / G);
+    int64_t blocks = (warps_needed + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    const int grid = (int)blocks;
+    switch (G) {
+        case 1: launch_step_gc<1, 1>(a, grid, st); break;
+        case 2: launch_step_gc<2, 1>(a, grid, st); break;
+        case 4: launch_step_gc<4, 1>(a, grid, st); break;
+        case 8: launch_step_gc<8, 1>(a, grid, st); break;
+        case 16: launch_step_gc<16, 1>(a, grid, st); break;
+        default:
+            if (C == 1) launch_step_gc<32, 1>(a, grid, st);
+            else if (C == 2) launch_step_gc<32, 2>(a, grid, st);
+            else if (C == 3) launch_step_gc<32, 3>(a, grid, st);
+            else launch_step_gc<32, 4>(a, grid, st);
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// a6. TF1 Adam on IndexedSlices = dense sweep (AdamOptimizer._apply_sparse_shared):
+//   m <- b1 m + (1-b1) G ; v <- b2 v + (1-b2) G*G ; W <- W - lr_t m / (sqrt(v) + eps)
+// over EVERY row (G is zero on untouched rows).  One launch sweeps both tables; G is consumed
+// and zeroed for the next step.  lr_t is formed on the device from the fp32 beta-power
+// variables so a captured step needs no host value.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float adam_elem(float& w, float& m, float& v, float g, float lr_t) {
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
+    const float omb1 = fsub(1.0f, b1), omb2 = fsub(1.0f, b2);
+    m = fadd(fmul(m, b1), fmul(g, omb1));
+    v = fadd(fmul(v, b2), fmul(fmul(g, g), omb2));
+    w = fsub(w, fdiv(fmul(lr_t, m), fadd(fsqrt(v), eps)));
+    return w;
+}
+
+__global__ void __launch_bounds__(256) adam_dense_kernel(AdamArgs a) {
+    const float b1p = a.pw[0], b2p = a.pw[1];
+    const float lr_t = fdiv(fmul(a.lr, fsqrt(fsub(1.0f, b2p))), fsub(1.0f, b1p));
+    const int64_t n4 = a.n4[0] + a.n4[1];
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+        const bool t = e >= a.n4[0];
+        const int64_t k = t ? e - a.n4[0] : e;
+        float4* W = reinterpret_cast<float4*>(t ? a.W[1] : a.W[0]) + k;
+        float4* M = reinterpret_cast<float4*>(t ? a.m[1] : a.m[0]) + k;
+        float4* V = reinterpret_cast<float4*>(t ? a.v[1] : a.v[0]) + k;
+        float4* Gp = reinterpret_cast<float4*>(t ? a.G[1] : a.G[0]) + k;
+        float4 w = *W, m = *M, v = *V, g = *Gp;
+        adam_elem(w.x, m.x, v.x, g.x, lr_t);
+        adam_elem(w.y, m.y, v.y, g.y, lr_t);
+        adam_elem(w.z, m.z, v.z, g.z, lr_t);
+        adam_elem(w.w, m.w, v.w, g.w, lr_t);
+        *W = w; *M = m; *V = v;
+        *Gp = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+void launch_adam_dense(const AdamArgs& a, cudaStream_t st) {
+    int64_t n4 = a.n4[0] + a.n4[1];
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    adam_dense_kernel<<<(int)blocks, 256, 0, st>>>(a);
+}
+
+// loss3 = {loss, mf, reg}; beta powers advance (AdamOptimizer._finish); accumulators reset.
+__global__ void finish_step_kernel(double* loss_acc, float* loss3, float* pw, double B, double regs, double batch_size,
+                                   int advance_powers) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double mf = -loss_acc[0] / B;
+        double reg = regs * 0.5 * loss_acc[1] / batch_size;
+        loss3[0] = (float)(mf + reg); loss3[1] = (float)mf; loss3[2] = (float)reg;
+        loss_acc[0] = 0.0; loss_acc[1] = 0.0;
+        if (advance_powers) { pw[0] = fmul(pw[0], 0.9f); pw[1] = fmul(pw[1], 0.999f); }
+    }
+}
+
+void launch_finish_step(double* loss_acc, float* loss3, float* pw, int64_t B, float regs, int batch_size,
+                        int advance_powers, cudaStream_t st) {
+    finish_step_kernel<<<1, 32, 0, st>>>(loss_acc, loss3, pw, (double)B, (double)regs, (double)batch_size, advance_powers);
+}
+
+}  // namespace pda

@@ -1,0 +1,72 @@
+"""Data-parallel driver of the train step over the GPUs of one box.
+
+Partition: USERS are split into contiguous shards, one per rank; every rank samples its B triples from
+its own users (rank-local sampling), so user rows, user gradients and the user table's Adam state never
+leave the GPU.  The ITEM table (small: n_items x d) is replicated; its gradient is the one real exchange
+step: an NCCL all-reduce (sum) of the dense item-gradient accumulator between the fused BPR kernel and
+the Adam sweep, after which every rank applies the identical item update.  The result equals a
+single-process step on the union batch of world*B triples (loss mean and L2 divisor use the global batch).
+
+torch.distributed is plumbing: it owns the NCCL communicator and the stream; the kernels are the library's.
+With world == 1 this class adds nothing to the single-GPU path.
+"""
+from __future__ import annotations
+
+
+class _DevArray:
+    """Exposes a raw device pointer owned by libpda_b200 through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"data": (int(ptr), False), "shape": tuple(shape), "typestr": typestr,
+                                         "version": 2, "strides": None}
+
+
+def shard_range(n, world, rank):
+    """Contiguous shard [lo, hi) of n rows for `rank`; the first n % world ranks get one extra row."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class ShardedTrainer:
+    def __init__(self, model, world=1, rank=0, reducer=None):
+        """reducer(tensor) -> None sums `tensor` in place over ranks (default: torch.distributed.all_reduce)."""
+        self.model, self.world, self.rank = model, int(world), int(rank)
+        self._gi = self._acc = None
+        self._reduce = reducer
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+            if reducer is None:
+                self._reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            dev = torch.device("cuda", model.device)
+            self._gi = torch.as_tensor(_DevArray(model.grad_ptr("item_embedding"), (model.n_items, model.emb_dim), "<f4"),
+                                       device=dev)
+            self._acc = torch.as_tensor(_DevArray(model.loss_acc_ptr(), (2,), "<f8"), device=dev)
+
+    def _exchange(self):
+        self._reduce(self._gi)     # dense item-gradient block, summed over ranks (NVLink / NVSwitch)
+        self._reduce(self._acc)    # 2 doubles: loss partial sums -> global mean
+
+    def train_sampled(self, seed, epoch, step0, n_steps, B, stream=0):
+        m = self.model
+        if self.world == 1:
+            m.train_sampled(seed, epoch, step0, n_steps, B, stream)
+            return
+        m.set_global_batch(B * self.world)
+        for k in range(n_steps):
+            m.sample_batch(seed, epoch, step0 + k, B, stream, fetch=False)
+            m.forward_backward_device(B, stream)
+            self._exchange()
+            m.adam_apply(stream)
+
+    def train_step_host(self, users, pos, neg, pos_pop=None, neg_pop=None, stream=0):
+        m = self.model
+        if self.world == 1:
+            return m.train_step(users, pos, neg, pos_pop, neg_pop)
+        m.set_global_batch(len(users) * self.world)
+        B = m.stage_batch(users, pos, neg, pos_pop, neg_pop, stream)
+        m.forward_backward_device(B, stream)
+        self._exchange()
+        m.adam_apply(stream)
+        return m.read_loss(stream)

@@ -1,0 +1,19 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with `pytest -m gpu` through gpurun)")
+
+
+@pytest.fixture(scope="session")
+def c_oracle():
+    from oracle import c_oracle as co
+    co.build()
+    return co

@@ -1,0 +1,92 @@
+"""GPU parity of scoring + mask + top-K + metrics (through the C ABI) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from helpers import synth_interactions
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pda():
+    import pda_b200
+    assert pda_b200.load().pda_device_count() >= 1, "no CUDA device visible: GPU tests cannot run"
+    return pda_b200
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.int32)
+
+
+def _setup(pda, n_users, n_items, d, seed, scale=1.0):
+    from oracle import pda_oracle as po
+    rng = np.random.default_rng(seed)
+    U = (rng.normal(0, scale, (n_users, d)) / np.sqrt(d)).astype(np.float32)
+    I = (rng.normal(0, scale, (n_items, d)) / np.sqrt(d)).astype(np.float32)
+    uid, iid, t = synth_interactions(n_users, n_items, 20, 9, seed=seed + 1, empty_frac=0.05)
+    indptr, items, times = po.build_csr(n_users, uid, iid, t)
+    pop = (rng.random(n_items) ** 2).astype(np.float32)
+    pop[rng.random(n_items) < 0.15] = 0.0      # exact zeros -> many ties at 0
+    m = pda.PDAModel(n_users, n_items, d, train="s_condition", batch_size=64, init=False)
+    m.set_table("user_embedding", U)
+    m.set_table("item_embedding", I)
+    m.set_train_csr(indptr, items, times)
+    return m, U, I, indptr, items, pop, rng
+
+
+@pytest.mark.parametrize("n_users,n_items,d,K", [(300, 1000, 64, 50), (130, 257, 32, 20), (64, 4000, 128, 50),
+                                                 (70, 40, 16, 50), (90, 700, 20, 128)])
+@pytest.mark.parametrize("rec_type", ["main_branch", "condition"])
+def test_recommend_exact_bit_exact(pda, c_oracle, n_users, n_items, d, K, rec_type):
+    m, U, I, indptr, items, pop, rng = _setup(pda, n_users, n_items, d, seed=n_items, scale=3.0)
+    users = rng.permutation(n_users)[: max(1, n_users - 7)].astype(np.int32)
+    ids, sc = m.do_recommendation(users, None, rec_type, pos_pop=pop, K=K, backend="exact", return_scores=True)
+    rid, rsc = c_oracle.recommend(U, I, users, rec_type, K, indptr, items, pop=pop)
+    assert np.array_equal(ids, rid)
+    assert np.array_equal(bits(sc), bits(rsc))
+    # no train item is ever recommended while unmasked items remain (train_new_api.py:597)
+    for r, u in enumerate(users[:50]):
+        row = items[indptr[u]:indptr[u + 1]]
+        n_free = n_items - len(np.unique(row))
+        assert not np.isin(ids[r][: min(K, n_free)], row).any()
+    m.close()
+
+
+def test_recommend_without_mask_and_with_bias(pda, c_oracle):
+    m, U, I, indptr, items, pop, rng = _setup(pda, 200, 900, 64, seed=3)
+    users = np.arange(200, dtype=np.int32)
+    bias = rng.normal(0, 0.1, 900).astype(np.float32)
+    ids, sc = m.do_recommendation(users, None, "main_branch", K=50, mask=False, col_bias=bias, backend="exact",
+                                  return_scores=True)
+    rid, rsc = c_oracle.recommend(U, I, users, "main_branch", 50, None, None, col_bias=bias)
+    assert np.array_equal(ids, rid) and np.array_equal(bits(sc), bits(rsc))
+    m.close()
+
+
+def test_dense_scores_match_oracle(pda):
+    from oracle import pda_oracle as po
+    m, U, I, indptr, items, pop, rng = _setup(pda, 100, 300, 64, seed=8)
+    users = rng.permutation(100)[:70].astype(np.int32)
+    S = m.testing(users, None, "main_branch")
+    assert np.array_equal(bits(S), bits(po.exact_scores(U[users], I)))
+    Y = m.testing(users, None, "condition", pos_pop=pop)
+    assert np.array_equal(bits(Y), bits(po.transform_scores(po.exact_scores(U[users], I), "condition", pop)))
+    m.set_testing_way("condition", pop)
+    assert np.array_equal(bits(m.predict(users, None)), bits(Y))
+    m.close()
+
+
+def test_metrics_match_oracle(pda, c_oracle):
+    from oracle import pda_oracle as po
+    rng = np.random.default_rng(2)
+    n_users, n_items, M, K = 500, 300, 321, 50
+    uid, iid, _ = synth_interactions(n_users, n_items, 6, 1, seed=4, empty_frac=0.1)
+    tptr, titems, _ = po.build_csr(n_users, uid, iid)
+    eval_users = rng.permutation(n_users)[:M].astype(np.int32)
+    ids = np.stack([rng.permutation(n_items)[:K] for _ in range(M)]).astype(np.int32)
+    m = pda.PDAModel(n_users, n_items, 8)
+    got = m.metrics_sum(ids, eval_users, tptr, titems, [20, 50])
+    want = c_oracle.metrics_sum(ids, eval_users, tptr, titems, [20, 50])
+    for k in want:
+        assert np.allclose(got[k], want[k], rtol=1e-12, atol=1e-12), k
+    m.close()
