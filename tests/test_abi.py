@@ -1,0 +1,116 @@
+"""The C-ABI boundary without a GPU: libpda_b200.so loads, exports every symbol include/pda_b200.h declares,
+the ctypes prototype table mirrors the header one to one, and the product path fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "pda_b200.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    src = re.sub(r"^\s*#.*$", "", src, flags=re.M)
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][\w\s\*]*?)\b(pda_\w+)\s*\(([^;{}]*)\)\s*;", src):
+        args = m.group(3).strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        out[m.group(2)] = n
+    return out
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import pda_b200
+    return pda_b200.load()
+
+
+def test_header_declares_the_expected_surface():
+    fns = header_functions()
+    for need in ("pda_create", "pda_destroy", "pda_train_step_host", "pda_train_step_device", "pda_sample_batch",
+                 "pda_recommend_host", "pda_recommend_device", "pda_scores_host", "pda_metrics_host", "pda_adam_apply",
+                 "pda_forward_backward_device", "pda_last_error"):
+        assert need in fns, need
+    assert len(fns) >= 30
+
+
+def test_library_exports_every_declared_symbol(lib):
+    for name in header_functions():
+        assert hasattr(lib, name), f"{name} declared in include/pda_b200.h but not exported by libpda_b200.so"
+
+
+def test_ctypes_prototypes_mirror_the_header():
+    from pda_b200 import _lib
+    fns = header_functions()
+    assert set(_lib.PROTOTYPES) == set(fns), set(_lib.PROTOTYPES) ^ set(fns)
+    for name, (_, argtypes) in _lib.PROTOTYPES.items():
+        assert len(argtypes) == fns[name], f"{name}: header has {fns[name]} args, binding has {len(argtypes)}"
+
+
+def test_exported_symbols_are_plain_c(lib):
+    """extern "C": the pda_* entry points appear unmangled in the dynamic symbol table; nothing of torch / the
+    oracle is linked in."""
+    from pda_b200 import _lib
+    dyn = subprocess.run(["nm", "-D", "--defined-only", _lib.SO_PATH], capture_output=True, text=True).stdout
+    names = {ln.split()[-1] for ln in dyn.splitlines() if ln.strip()}
+    for name in header_functions():
+        assert name in names
+    needed = subprocess.run(["readelf", "-d", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "torch" not in needed and "pda_oracle" not in needed and "python" not in needed.lower()
+
+
+def test_config_struct_layout_matches_header():
+    from pda_b200._lib import PdaConfig
+    # device i32 | pad | n_users i64 | n_items i64 | embed_size i32 | train_mode i32 | batch_size i32 | lr f32 |
+    # regs f32 | pad | max_batch i64   (natural alignment of the C struct in include/pda_b200.h)
+    assert PdaConfig.n_users.offset == 8 and PdaConfig.n_items.offset == 16 and PdaConfig.embed_size.offset == 24
+    assert PdaConfig.lr.offset == 36 and PdaConfig.regs.offset == 40 and PdaConfig.max_batch.offset == 48
+    assert C.sizeof(PdaConfig) == 56
+
+
+def test_version_and_error_string(lib):
+    assert lib.pda_version() >= 100
+    assert isinstance(lib.pda_last_error(), bytes)
+
+
+def test_no_cpu_fallback_without_a_gpu(lib):
+    """pda_create must fail with PDA_ERR_CUDA when no B200 is visible; the Python mirror raises PdaError."""
+    if lib.pda_device_count() > 0:
+        pytest.skip("a GPU is visible: the loud-failure path is not reachable")
+    import pda_b200
+    from pda_b200._lib import PdaConfig
+    cfg = PdaConfig(0, 10, 10, 8, 0, 4, 1e-3, 1e-5, 0)
+    h = C.c_void_p()
+    rc = lib.pda_create(C.byref(cfg), C.byref(h))
+    assert rc == 2 and not h.value
+    assert b"no CPU fallback" in lib.pda_last_error()
+    with pytest.raises(pda_b200.PdaError, match="no CPU fallback"):
+        pda_b200.PDAModel(10, 10, 8)
+
+
+def test_argument_validation_happens_before_cuda(lib):
+    from pda_b200._lib import PdaConfig
+    h = C.c_void_p()
+    for bad in (PdaConfig(0, 10, 10, 7, 0, 4, 1e-3, 1e-5, 0),      # embed_size % 4
+                PdaConfig(0, 0, 10, 8, 0, 4, 1e-3, 1e-5, 0),       # n_users < 1
+                PdaConfig(0, 10, 10, 8, 9, 4, 1e-3, 1e-5, 0)):     # unknown train_mode
+        assert lib.pda_create(C.byref(bad), C.byref(h)) == 1       # PDA_ERR_ARG
+        assert lib.pda_last_error()
+    assert lib.pda_create(None, C.byref(h)) == 1
+
+
+def test_product_package_never_imports_the_oracle():
+    """only tests/, __graft_entry__.smoke() and bench.py's CPU legs may touch oracle/ (it is the checker)."""
+    for base in ("pda_b200", "MF"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, base)):
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                    txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                    assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dirpath, f)
+                    assert not re.search(r"#include[^\n]*oracle|libpda_oracle|libref_eval", txt), os.path.join(dirpath, f)
