@@ -40,6 +40,7 @@ extern "C" {
 /* --train of MF/parse.py:11 */
 #define PDA_TRAIN_NORMAL 0      /* BPRMF           : create_bpr_loss                (model_api.py:695-706) */
 #define PDA_TRAIN_S_CONDITION 1 /* PD / PDA / PDG  : create_bpr_loss_with_pop_global (model_api.py:102-121) */
+#define PDA_TRAIN_TEMP_POP 2    /* BPR(t)-pop      : BPRMFTempPop (model_api.py:300-401); TF-GPU gather_nd semantics */
 
 /* rec_type of do_recommendation (train_new_api.py:626-633) */
 #define PDA_REC_MAIN_BRANCH 0   /* y = u.i                      (PD, BPRMF)   */
@@ -52,6 +53,13 @@ extern "C" {
 #define PDA_TABLE_USER_V 3
 #define PDA_TABLE_ITEM_M 4
 #define PDA_TABLE_ITEM_V 5
+/* BPR(t)-pop only: user_temp_bias [n_users, 1], item_temp_init_bias [n_items, temp_num + 1] and their Adam slots */
+#define PDA_TABLE_USER_BIAS 6
+#define PDA_TABLE_ITEM_BIAS 7
+#define PDA_TABLE_USER_BIAS_M 8
+#define PDA_TABLE_USER_BIAS_V 9
+#define PDA_TABLE_ITEM_BIAS_M 10
+#define PDA_TABLE_ITEM_BIAS_V 11
 
 /* eval back end */
 #define PDA_EVAL_AUTO 0
@@ -70,6 +78,7 @@ typedef struct pda_config {
     float lr;            /* --lr */
     float regs;          /* --regs */
     int64_t max_batch;   /* capacity of the internal batch buffers (0 -> batch_size) */
+    int32_t temp_num;    /* PDA_TRAIN_TEMP_POP: number of train stages T = data_config['temp_num'] (else ignored) */
 } pda_config;
 
 const char* pda_last_error(void);
@@ -126,7 +135,10 @@ int pda_get_batch(pda_model* m, int64_t B, int32_t* users, int32_t* pos, int32_t
                   float* neg_pop);
 
 /* one optimisation step -- replaces sess.run([opt, loss, mf_loss, reg_loss]) (train_new_api.py:1080-1090).
- * loss3_out = {loss, mf_loss, reg_loss}.  pos_pop/neg_pop are ignored for PDA_TRAIN_NORMAL. */
+ * loss3_out = {loss, mf_loss, reg_loss}.  pos_pop/neg_pop are ignored for PDA_TRAIN_NORMAL.  For
+ * PDA_TRAIN_TEMP_POP the two fp32 slots carry what the reference's iterator carries in them
+ * (train_new_api.py:544-545,563-565): pos_pop = the stage `temp` of each triple as fp32 (cast to int32 on the
+ * device), neg_pop = `raw` (= arange(B); may be NULL, never read). */
 int pda_train_step_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                         const float* pos_pop, const float* neg_pop, int64_t B, float* loss3_out);
 /* device pointers; users == NULL -> use the internal batch written by pda_sample_batch */
@@ -151,10 +163,20 @@ int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos,
                          const float* pos_pop, const float* neg_pop, int64_t B, void* stream);
 /* loss3 of the last enqueued step (synchronises `stream`) */
 int pda_read_loss(pda_model* m, float* loss3_out, void* stream);
+/* running sums of the per-step fp32 {loss, mf_loss, reg_loss} in double + the step count since the last
+ * reset -- the epoch means of train_new_api.py:1095-1097 without a host sync per step (synchronises `stream`) */
+int pda_read_loss_sums(pda_model* m, double* out4, int reset, void* stream);
 /* forward/backward only (no optimizer): gradients of the two tables as dense [rows, d] host arrays; test hook */
 int pda_gradients_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                        const float* pos_pop, const float* neg_pop, int64_t B, float* gU_out, float* gI_out,
                        float* loss3_out);
+
+/* BPR(t)-pop test hook: like pda_gradients_host plus the bias gradients gub [n_users], gib [n_items, temp_num+1] */
+int pda_gradients_temp_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* temp,
+                            int64_t B, float* gU_out, float* gI_out, float* gub_out, float* gib_out, float* loss3_out);
+/* BPR(t)-pop inference bias of one eval batch (model_api.py:373-387): out[j] = (1 + user_temp_bias[first_user]) *
+ * (item_bias[j, T-1] + item_bias[j, T]), fp32 [n_items] on the host; pass it as col_bias of pda_recommend_* */
+int pda_temp_item_bias_host(pda_model* m, int32_t first_user, float* out);
 
 /* recommendation -- replaces do_recommendation (train_new_api.py:614-640).  users: M global user ids;
  * all n_items are scored; pop: fp32 [n_items] (PDA_REC_WITH_POP) or NULL; col_bias: optional fp32

@@ -26,7 +26,7 @@ class PdaError(RuntimeError):
 class PdaConfig(C.Structure):
     _fields_ = [("device", C.c_int32), ("n_users", C.c_int64), ("n_items", C.c_int64), ("embed_size", C.c_int32),
                 ("train_mode", C.c_int32), ("batch_size", C.c_int32), ("lr", C.c_float), ("regs", C.c_float),
-                ("max_batch", C.c_int64)]
+                ("max_batch", C.c_int64), ("temp_num", C.c_int32)]
 
 
 # name -> (restype, argtypes); mirrors include/pda_b200.h one to one
@@ -62,7 +62,10 @@ PROTOTYPES = {
     "pda_adam_apply": (C.c_int, [c_vp, c_vp]),
     "pda_stage_batch_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp]),
     "pda_read_loss": (C.c_int, [c_vp, c_vp, c_vp]),
+    "pda_read_loss_sums": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
     "pda_gradients_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp, c_vp, c_vp]),
+    "pda_gradients_temp_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "pda_temp_item_bias_host": (C.c_int, [c_vp, C.c_int32, c_vp]),
     "pda_recommend_host": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp]),
     "pda_recommend_device": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp,
                                        c_vp]),

@@ -35,10 +35,13 @@ struct pda_model {
     pda_config cfg;
     int64_t nU, nI;
     int d;
-    float *W[2], *Mo[2], *Vo[2], *G[2];   // 0 = user table, 1 = item table
+    float *W[4], *Mo[4], *Vo[4], *G[4];   // 0 = user table, 1 = item table, 2 = user_temp_bias, 3 = item_temp_init_bias
+    int64_t rows[4]; int cols[4]; int64_t n4[4];   // logical shape and padded float4 count of each array
+    int n_arr;                                      // 2, or 4 for BPR(t)-pop
     float* pw;          // {beta1_power, beta2_power}
     double* loss_acc;   // {sum log(sigmoid+1e-10), sum of squares}
     float* loss3;       // device {loss, mf, reg}
+    double* loss_sum;   // device {sum loss, sum mf, sum reg, steps} since the last pda_read_loss_sums(reset)
     float* loss3_pinned;
     // train CSR / mask
     int64_t* indptr; int32_t* items; uint8_t* times; int64_t nnz;
@@ -53,6 +56,7 @@ struct pda_model {
     void* stage_pinned; size_t stage_bytes;
     // eval scratch
     void* ev_buf; size_t ev_bytes;
+    float* grad_bias_out[2];   // pda_gradients_temp_host: host destinations of the bias gradients
     void* ev_pinned; size_t ev_pinned_bytes;
     // optional per-kernel CUDA-event timing (pda_profile_*): [kernel kind][slot][begin/end]
     int prof_on; int prof_n[PDA_PROF_KINDS];
@@ -115,8 +119,11 @@ int pda_create(const pda_config* cfg, pda_model** out) {
         return fail(PDA_ERR_ARG, "n_users, n_items and batch_size must be positive");
     if (cfg->n_users > 0x7fffffffLL || cfg->n_items > 0x7fffffffLL)
         return fail(PDA_ERR_ARG, "ids are int32: n_users/n_items must be < 2^31");
-    if (cfg->train_mode != PDA_TRAIN_NORMAL && cfg->train_mode != PDA_TRAIN_S_CONDITION)
+    if (cfg->train_mode != PDA_TRAIN_NORMAL && cfg->train_mode != PDA_TRAIN_S_CONDITION &&
+        cfg->train_mode != PDA_TRAIN_TEMP_POP)
         return fail(PDA_ERR_ARG, "unknown train_mode %d", cfg->train_mode);
+    if (cfg->train_mode == PDA_TRAIN_TEMP_POP && (cfg->temp_num < 1 || cfg->temp_num > 255))
+        return fail(PDA_ERR_ARG, "train_mode temp_pop needs temp_num in [1, 255], got %d", cfg->temp_num);
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -135,18 +142,21 @@ int pda_create(const pda_config* cfg, pda_model** out) {
     m->cfg = *cfg;
     m->nU = cfg->n_users; m->nI = cfg->n_items; m->d = cfg->embed_size;
     m->cap = cfg->max_batch > 0 ? cfg->max_batch : cfg->batch_size;
-    const int64_t rows[2] = {m->nU, m->nI};
-    for (int t = 0; t < 2; ++t) {
-        size_t n = (size_t)rows[t] * m->d;
+    m->n_arr = cfg->train_mode == PDA_TRAIN_TEMP_POP ? 4 : 2;
+    m->rows[0] = m->nU; m->cols[0] = m->d; m->rows[1] = m->nI; m->cols[1] = m->d;
+    m->rows[2] = m->nU; m->cols[2] = 1; m->rows[3] = m->nI; m->cols[3] = cfg->temp_num + 1;
+    for (int t = 0; t < m->n_arr; ++t) {
+        m->n4[t] = (m->rows[t] * m->cols[t] + 3) / 4;   // padded to whole float4s (the pad stays zero)
+        size_t n = (size_t)m->n4[t] * 4;
         CK(dmalloc(&m->W[t], n)); CK(dmalloc(&m->Mo[t], n)); CK(dmalloc(&m->Vo[t], n)); CK(dmalloc(&m->G[t], n));
         CK(cudaMemset(m->W[t], 0, n * 4)); CK(cudaMemset(m->Mo[t], 0, n * 4));
         CK(cudaMemset(m->Vo[t], 0, n * 4)); CK(cudaMemset(m->G[t], 0, n * 4));
     }
-    CK(dmalloc(&m->pw, 2)); CK(dmalloc(&m->loss_acc, 2)); CK(dmalloc(&m->loss3, 4));
+    CK(dmalloc(&m->pw, 2)); CK(dmalloc(&m->loss_acc, 2)); CK(dmalloc(&m->loss3, 4)); CK(dmalloc(&m->loss_sum, 4));
     const float pw0[2] = {0.9f, 0.999f};
     CK(cudaMemcpy(m->pw, pw0, 8, cudaMemcpyHostToDevice));
-    CK(cudaMemset(m->loss_acc, 0, 16)); CK(cudaMemset(m->loss3, 0, 16));
-    CK(cudaHostAlloc((void**)&m->loss3_pinned, 16, cudaHostAllocDefault));
+    CK(cudaMemset(m->loss_acc, 0, 16)); CK(cudaMemset(m->loss3, 0, 16)); CK(cudaMemset(m->loss_sum, 0, 32));
+    CK(cudaHostAlloc((void**)&m->loss3_pinned, 64, cudaHostAllocDefault));
     CK(dmalloc(&m->b_users, (size_t)m->cap)); CK(dmalloc(&m->b_pos, (size_t)m->cap)); CK(dmalloc(&m->b_neg, (size_t)m->cap));
     CK(dmalloc(&m->b_time, (size_t)m->cap)); CK(dmalloc(&m->b_pp, (size_t)m->cap)); CK(dmalloc(&m->b_np, (size_t)m->cap));
     CK(cudaDeviceSynchronize());
@@ -158,8 +168,8 @@ void pda_destroy(pda_model* m) {
     if (!m) return;
     cudaSetDevice(m->cfg.device);
     cudaDeviceSynchronize();
-    for (int t = 0; t < 2; ++t) { cudaFree(m->W[t]); cudaFree(m->Mo[t]); cudaFree(m->Vo[t]); cudaFree(m->G[t]); }
-    cudaFree(m->pw); cudaFree(m->loss_acc); cudaFree(m->loss3); cudaFreeHost(m->loss3_pinned);
+    for (int t = 0; t < 4; ++t) { cudaFree(m->W[t]); cudaFree(m->Mo[t]); cudaFree(m->Vo[t]); cudaFree(m->G[t]); }
+    cudaFree(m->pw); cudaFree(m->loss_acc); cudaFree(m->loss3); cudaFree(m->loss_sum); cudaFreeHost(m->loss3_pinned);
     cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
     cudaFree(m->pop_train);
     cudaFree(m->b_users); cudaFree(m->b_pos); cudaFree(m->b_neg); cudaFree(m->b_time); cudaFree(m->b_pp); cudaFree(m->b_np);
@@ -214,31 +224,41 @@ int pda_synchronize(pda_model* m) {
 int pda_init_tables(pda_model* m, uint32_t seed) {
     if (!m) return fail(PDA_ERR_ARG, "null model");
     CK(cudaSetDevice(m->cfg.device));
-    launch_xavier_init(m->W[0], m->nU, m->d, seed, 0u, 0);
-    launch_xavier_init(m->W[1], m->nI, m->d, seed, 1u, 0);
+    for (int t = 0; t < m->n_arr; ++t) launch_xavier_init(m->W[t], m->rows[t], m->cols[t], seed, (uint32_t)t, 0);
     CK(cudaGetLastError());
-    const int64_t rows[2] = {m->nU, m->nI};
-    for (int t = 0; t < 2; ++t) {
-        size_t n = (size_t)rows[t] * m->d * 4;
+    for (int t = 0; t < m->n_arr; ++t) {
+        size_t n = (size_t)m->n4[t] * 16;
         CK(cudaMemsetAsync(m->Mo[t], 0, n)); CK(cudaMemsetAsync(m->Vo[t], 0, n)); CK(cudaMemsetAsync(m->G[t], 0, n));
     }
     const float pw0[2] = {0.9f, 0.999f};
     CK(cudaMemcpy(m->pw, pw0, 8, cudaMemcpyHostToDevice));
     CK(cudaMemset(m->loss_acc, 0, 16));
+    CK(cudaMemset(m->loss_sum, 0, 32));
     CK(cudaDeviceSynchronize());
     return PDA_OK;
 }
 
-static float* table_of(pda_model* m, int which, int64_t* rows) {
+// *n = number of fp32 elements of the selected array (rows x cols)
+static float* table_of(pda_model* m, int which, int64_t* n) {
+    int t, kind;   // kind 0 = variable, 1 = Adam m, 2 = Adam v
     switch (which) {
-        case PDA_TABLE_USER: *rows = m->nU; return m->W[0];
-        case PDA_TABLE_ITEM: *rows = m->nI; return m->W[1];
-        case PDA_TABLE_USER_M: *rows = m->nU; return m->Mo[0];
-        case PDA_TABLE_USER_V: *rows = m->nU; return m->Vo[0];
-        case PDA_TABLE_ITEM_M: *rows = m->nI; return m->Mo[1];
-        case PDA_TABLE_ITEM_V: *rows = m->nI; return m->Vo[1];
+        case PDA_TABLE_USER: t = 0; kind = 0; break;
+        case PDA_TABLE_ITEM: t = 1; kind = 0; break;
+        case PDA_TABLE_USER_M: t = 0; kind = 1; break;
+        case PDA_TABLE_USER_V: t = 0; kind = 2; break;
+        case PDA_TABLE_ITEM_M: t = 1; kind = 1; break;
+        case PDA_TABLE_ITEM_V: t = 1; kind = 2; break;
+        case PDA_TABLE_USER_BIAS: t = 2; kind = 0; break;
+        case PDA_TABLE_ITEM_BIAS: t = 3; kind = 0; break;
+        case PDA_TABLE_USER_BIAS_M: t = 2; kind = 1; break;
+        case PDA_TABLE_USER_BIAS_V: t = 2; kind = 2; break;
+        case PDA_TABLE_ITEM_BIAS_M: t = 3; kind = 1; break;
+        case PDA_TABLE_ITEM_BIAS_V: t = 3; kind = 2; break;
+        default: return nullptr;
     }
-    return nullptr;
+    if (t >= m->n_arr) return nullptr;
+    *n = m->rows[t] * m->cols[t];
+    return kind == 0 ? m->W[t] : kind == 1 ? m->Mo[t] : m->Vo[t];
 }
 
 int pda_set_table(pda_model* m, int which, const float* src) {
@@ -246,7 +266,7 @@ int pda_set_table(pda_model* m, int which, const float* src) {
     int64_t rows; float* p = table_of(m, which, &rows);
     if (!p) return fail(PDA_ERR_ARG, "unknown table %d", which);
     CK(cudaSetDevice(m->cfg.device));
-    CK(cudaMemcpy(p, src, (size_t)rows * m->d * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(p, src, (size_t)rows * 4, cudaMemcpyHostToDevice));
     return PDA_OK;
 }
 int pda_get_table(pda_model* m, int which, float* dst) {
@@ -255,7 +275,7 @@ int pda_get_table(pda_model* m, int which, float* dst) {
     if (!p) return fail(PDA_ERR_ARG, "unknown table %d", which);
     CK(cudaSetDevice(m->cfg.device));
     CK(cudaDeviceSynchronize());
-    CK(cudaMemcpy(dst, p, (size_t)rows * m->d * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(dst, p, (size_t)rows * 4, cudaMemcpyDeviceToHost));
     return PDA_OK;
 }
 void* pda_table_ptr(pda_model* m, int which) {
@@ -362,6 +382,7 @@ static int do_sample(pda_model* m, uint32_t seed, uint32_t epoch, uint32_t step,
     if (m->cfg.train_mode == PDA_TRAIN_S_CONDITION && !m->pop_train)
         return fail(PDA_ERR_STATE, "train_mode s_condition needs pda_set_train_pop");
     if (m->pop_train && m->T_pop > 1 && !m->times) return fail(PDA_ERR_STATE, "time-dependent popularity needs interaction times");
+    if (m->cfg.train_mode == PDA_TRAIN_TEMP_POP && !m->times) return fail(PDA_ERR_STATE, "train_mode temp_pop needs interaction times");
     SamplerArgs a;
     memset(&a, 0, sizeof(a));
     a.seed = seed; a.epoch = epoch; a.step = step; a.B = B;
@@ -411,8 +432,16 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
     m->last_B = m->global_batch > 0 ? m->global_batch : B;
     s.invB = 1.0f / (float)m->last_B;
     s.loss_acc = m->loss_acc;
-    s.pop_mode = m->cfg.train_mode == PDA_TRAIN_S_CONDITION;
+    s.pop_mode = m->cfg.train_mode == PDA_TRAIN_S_CONDITION ? 1 : m->cfg.train_mode == PDA_TRAIN_TEMP_POP ? 2 : 0;
     s.uniq_users = uniq;
+    if (s.pop_mode == 2) {   // BPR(t)-pop: the stage of each triple rides in the internal batch (b_time)
+        if (pp) {   // explicit batch: the reference passes `temp` as fp32 through the pos_pop slot (train_new_api.py:544,565)
+            if (B > m->cap) return fail(PDA_ERR_ARG, "B exceeds the batch capacity");
+            launch_f32_to_i32(pp, m->b_time, B, m->cfg.temp_num - 1, st);
+        }
+        s.temp = m->b_time; s.temp_num = m->cfg.temp_num;
+        s.ub = m->W[2]; s.ib = m->W[3]; s.Gub = m->G[2]; s.Gib = m->G[3];
+    }
     ProfScope ps(m, PDA_PROF_STEP, st);
     if (launch_bpr_step(s, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
     return PDA_OK;
@@ -422,13 +451,15 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
 static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st) {
     if (apply_adam) {
         AdamArgs a;
-        for (int t = 0; t < 2; ++t) { a.W[t] = m->W[t]; a.m[t] = m->Mo[t]; a.v[t] = m->Vo[t]; a.G[t] = m->G[t]; }
-        a.n4[0] = m->nU * m->d / 4; a.n4[1] = m->nI * m->d / 4;
+        memset(&a, 0, sizeof(a));
+        for (int t = 0; t < m->n_arr; ++t) {
+            a.W[t] = m->W[t]; a.m[t] = m->Mo[t]; a.v[t] = m->Vo[t]; a.G[t] = m->G[t]; a.n4[t] = m->n4[t];
+        }
         a.pw = m->pw; a.lr = m->cfg.lr;
         ProfScope ps(m, PDA_PROF_ADAM, st);
         launch_adam_dense(a, st);
     }
-    launch_finish_step(m->loss_acc, m->loss3, m->pw, m->last_B, m->cfg.regs, m->cfg.batch_size, apply_adam ? 1 : 0, st);
+    launch_finish_step(m->loss_acc, m->loss3, m->loss_sum, m->pw, m->last_B, m->cfg.regs, m->cfg.batch_size, apply_adam ? 1 : 0, st);
     return PDA_OK;
 }
 
@@ -462,8 +493,9 @@ int pda_forward_backward_device(pda_model* m, const int32_t* users, const int32_
     if (!users) {
         if (B < 1 || B > m->cap) return fail(PDA_ERR_ARG, "B exceeds the batch capacity");
         users = m->b_users; pos = m->b_pos; neg = m->b_neg; pp = m->b_pp; np_ = m->b_np;
+        if (m->cfg.train_mode == PDA_TRAIN_TEMP_POP) pp = np_ = nullptr;   // stages already sit in b_time
         uniq = m->batch_uniq;
-    }
+    } else if (m->cfg.train_mode == PDA_TRAIN_TEMP_POP && !pp) return fail(PDA_ERR_ARG, "temp_pop needs the stage array in the pos_pop slot");
     if (!pos || !neg) return fail(PDA_ERR_ARG, "null index pointer");
     if (m->cfg.train_mode == PDA_TRAIN_S_CONDITION && (!pp || !np_)) return fail(PDA_ERR_ARG, "s_condition needs pos_pop/neg_pop");
     int rc = enqueue_fwd_bwd(m, users, pos, neg, pp, np_, B, uniq, (cudaStream_t)stream);
@@ -492,8 +524,9 @@ int pda_train_step_device(pda_model* m, const int32_t* users, const int32_t* pos
     if (!users) {   // internal batch from the device sampler: users are distinct iff B <= #active users
         if (B < 1 || B > m->cap) return fail(PDA_ERR_ARG, "B exceeds the batch capacity");
         users = m->b_users; pos = m->b_pos; neg = m->b_neg; pp = m->b_pp; np_ = m->b_np;
+        if (m->cfg.train_mode == PDA_TRAIN_TEMP_POP) pp = np_ = nullptr;   // stages already sit in b_time
         uniq = m->batch_uniq;
-    }
+    } else if (m->cfg.train_mode == PDA_TRAIN_TEMP_POP && !pp) return fail(PDA_ERR_ARG, "temp_pop needs the stage array in the pos_pop slot");
     if (!pos || !neg) return fail(PDA_ERR_ARG, "null index pointer");
     if (m->cfg.train_mode == PDA_TRAIN_S_CONDITION && (!pp || !np_)) return fail(PDA_ERR_ARG, "s_condition needs pos_pop/neg_pop");
     int rc = enqueue_step(m, users, pos, neg, pp, np_, B, uniq, true, (cudaStream_t)stream);
@@ -505,7 +538,9 @@ int pda_train_step_device(pda_model* m, const int32_t* users, const int32_t* pos
 static int stage_batch(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
                        const float* np_, int64_t B, cudaStream_t st) {
     if (B < 1 || B > m->cap) return fail(PDA_ERR_ARG, "B=%lld exceeds the batch capacity %lld", (long long)B, (long long)m->cap);
-    const bool pop = m->cfg.train_mode == PDA_TRAIN_S_CONDITION;
+    const bool temp = m->cfg.train_mode == PDA_TRAIN_TEMP_POP;
+    const bool pop = m->cfg.train_mode == PDA_TRAIN_S_CONDITION || temp;   // two fp32 side arrays travel with the batch
+    if (temp && pp && !np_) np_ = pp;                                       // `raw` (= arange(B)) is never read
     if (!users || !pos || !neg || (pop && (!pp || !np_))) return fail(PDA_ERR_ARG, "null batch pointer");
     // one pinned staging block, one DMA per array
     m->batch_uniq = 0;
@@ -563,7 +598,9 @@ int pda_train_steps_sampled(pda_model* m, uint32_t seed, uint32_t epoch, uint32_
     for (int32_t k = 0; k < n_steps; ++k) {
         int rc = do_sample(m, seed, epoch, step0 + (uint32_t)k, B, st);
         if (rc) return rc;
-        rc = enqueue_step(m, m->b_users, m->b_pos, m->b_neg, m->b_pp, m->b_np, B, m->batch_uniq, true, st);
+        const bool tmode = m->cfg.train_mode == PDA_TRAIN_TEMP_POP;
+        rc = enqueue_step(m, m->b_users, m->b_pos, m->b_neg, tmode ? nullptr : m->b_pp, tmode ? nullptr : m->b_np, B,
+                          m->batch_uniq, true, st);
         if (rc) return rc;
     }
     CK(cudaGetLastError());
@@ -580,6 +617,18 @@ int pda_read_loss(pda_model* m, float* loss3_out, void* stream) {
     return PDA_OK;
 }
 
+int pda_read_loss_sums(pda_model* m, double* out4, int reset, void* stream) {
+    if (!m || !out4) return fail(PDA_ERR_ARG, "null argument");
+    CK(cudaSetDevice(m->cfg.device));
+    cudaStream_t st = (cudaStream_t)stream;
+    double* pin = (double*)((char*)m->loss3_pinned + 16);
+    CK(cudaMemcpyAsync(pin, m->loss_sum, 32, cudaMemcpyDeviceToHost, st));
+    if (reset) CK(cudaMemsetAsync(m->loss_sum, 0, 32, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(out4, pin, 32);
+    return PDA_OK;
+}
+
 int pda_gradients_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
                        const float* np_, int64_t B, float* gU_out, float* gI_out, float* loss3_out) {
     if (!m) return fail(PDA_ERR_ARG, "null model");
@@ -593,8 +642,33 @@ int pda_gradients_host(pda_model* m, const int32_t* users, const int32_t* pos, c
     if (gU_out) CK(cudaMemcpy(gU_out, m->G[0], (size_t)m->nU * m->d * 4, cudaMemcpyDeviceToHost));
     if (gI_out) CK(cudaMemcpy(gI_out, m->G[1], (size_t)m->nI * m->d * 4, cudaMemcpyDeviceToHost));
     if (loss3_out) CK(cudaMemcpy(loss3_out, m->loss3, 12, cudaMemcpyDeviceToHost));
-    CK(cudaMemset(m->G[0], 0, (size_t)m->nU * m->d * 4));
-    CK(cudaMemset(m->G[1], 0, (size_t)m->nI * m->d * 4));
+    if (m->n_arr == 4 && m->grad_bias_out[0]) CK(cudaMemcpy(m->grad_bias_out[0], m->G[2], (size_t)m->nU * 4, cudaMemcpyDeviceToHost));
+    if (m->n_arr == 4 && m->grad_bias_out[1])
+        CK(cudaMemcpy(m->grad_bias_out[1], m->G[3], (size_t)m->nI * (m->cfg.temp_num + 1) * 4, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < m->n_arr; ++t) CK(cudaMemset(m->G[t], 0, (size_t)m->n4[t] * 16));
+    return PDA_OK;
+}
+
+int pda_gradients_temp_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* temp,
+                            int64_t B, float* gU_out, float* gI_out, float* gub_out, float* gib_out, float* loss3_out) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    if (m->cfg.train_mode != PDA_TRAIN_TEMP_POP) return fail(PDA_ERR_STATE, "model is not in train_mode temp_pop");
+    m->grad_bias_out[0] = gub_out; m->grad_bias_out[1] = gib_out;
+    int rc = pda_gradients_host(m, users, pos, neg, temp, temp, B, gU_out, gI_out, loss3_out);
+    m->grad_bias_out[0] = m->grad_bias_out[1] = nullptr;
+    return rc;
+}
+
+int pda_temp_item_bias_host(pda_model* m, int32_t first_user, float* out) {
+    if (!m || !out) return fail(PDA_ERR_ARG, "null argument");
+    if (m->cfg.train_mode != PDA_TRAIN_TEMP_POP) return fail(PDA_ERR_STATE, "model is not in train_mode temp_pop");
+    if (first_user < 0 || first_user >= m->nU) return fail(PDA_ERR_ARG, "user id out of range");
+    CK(cudaSetDevice(m->cfg.device));
+    CK(ensure_dev(&m->ev_buf, &m->ev_bytes, (size_t)m->nI * 4));
+    launch_temp_item_bias(m->W[2], m->W[3], m->nI, m->cfg.temp_num, first_user, (float*)m->ev_buf, 0);
+    CK(cudaMemcpyAsync(out, m->ev_buf, (size_t)m->nI * 4, cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    CK(cudaGetLastError());
     return PDA_OK;
 }
 

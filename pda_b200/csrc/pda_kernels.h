@@ -26,13 +26,16 @@ struct StepArgs {
     float lb;     // regs / batch_size
     float invB;   // 1 / B
     double* loss_acc;
-    int pop_mode;     // 0: create_bpr_loss, 1: create_bpr_loss_with_pop_global
+    int pop_mode;     // 0: create_bpr_loss, 1: create_bpr_loss_with_pop_global, 2: BPRMFTempPop (model_api.py:336-371)
+    const int32_t* temp; int temp_num;          // mode 2: stage of each triple, number of train stages T
+    const float* ub; const float* ib;           // mode 2: user_temp_bias [n_users], item_temp_init_bias [n_items, T+1]
+    float* Gub; float* Gib;
     int uniq_users;   // users distinct within the batch -> plain stores for the user rows
 };
 
 struct AdamArgs {
-    float* W[2]; float* m[2]; float* v[2]; float* G[2];
-    int64_t n4[2];       // float4 count of each table
+    float* W[4]; float* m[4]; float* v[4]; float* G[4];   // user table, item table, [user bias, item bias]
+    int64_t n4[4];       // float4 count of each array (0 = unused)
     const float* pw;     // {beta1_power, beta2_power}
     float lr;
 };
@@ -53,8 +56,11 @@ void sampler_keys(uint32_t seed, uint32_t epoch, uint32_t step, uint32_t* keys);
 void launch_sampler(SamplerArgs a, cudaStream_t st);
 int launch_bpr_step(const StepArgs& a, cudaStream_t st);
 void launch_adam_dense(const AdamArgs& a, cudaStream_t st);
-void launch_finish_step(double* loss_acc, float* loss3, float* pw, int64_t B, float regs, int batch_size,
-                        int advance_powers, cudaStream_t st);
+void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float* pw, int64_t B, float regs,
+                        int batch_size, int advance_powers, cudaStream_t st);
+void launch_f32_to_i32(const float* src, int32_t* dst, int64_t n, int32_t max_value, cudaStream_t st);
+void launch_temp_item_bias(const float* ub, const float* ib, int64_t n_items, int temp_num, int32_t first_user,
+                           float* out, cudaStream_t st);
 int launch_recommend_exact(const EvalArgs& a, cudaStream_t st);
 void launch_metrics(const int32_t* ids, int64_t M, int Kkeep, const int32_t* eval_users, const int64_t* truth_indptr,
                     const int32_t* truth_items, const int32_t* Ks, int nK, double* out, cudaStream_t st);

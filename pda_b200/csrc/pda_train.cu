@@ -124,8 +124,9 @@ void launch_sampler(SamplerArgs a, cudaStream_t st) {
 // user row takes a plain store then).  Loss terms: per-lane partials -> warp shuffle ->
 // one fp64 atomic pair per warp.
 // ------------------------------------------------------------------------------------------
-template <int G, int C, bool POP, bool UNIQ>
+template <int G, int C, int MODE, bool UNIQ>
 __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
+    constexpr bool POP = MODE == 1, TEMP = MODE == 2;
     constexpr int GPW = 32 / G;  // triples per warp per iteration
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;       // lane within the group
@@ -141,9 +142,19 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
         const bool valid = i < a.B;
         int32_t iu = 0, ip = 0, in = 0;
         float pp = 1.0f, pn = 1.0f;
+        int32_t tt = 0;
+        float ubf = 1.0f, pib = 0.0f, nib = 0.0f;   // BPR(t)-pop bias terms (model_api.py:342-358)
         if (valid) {
             iu = __ldg(a.users + i); ip = __ldg(a.pos + i); in = __ldg(a.neg + i);
             if (POP) { pp = __ldg(a.pos_pop + i); pn = __ldg(a.neg_pop + i); }
+            if (TEMP) {
+                tt = __ldg(a.temp + i);
+                const int Tc = a.temp_num + 1;
+                // gather_nd(user_temp_bias_all[B,1], (row, t)) is out of bounds for t > 0 -> 0 (TF-GPU)
+                ubf = fadd(tt == 0 ? __ldg(a.ub + iu) : 0.0f, 1.0f);
+                pib = fadd(__ldg(a.ib + (int64_t)ip * Tc + a.temp_num), __ldg(a.ib + (int64_t)ip * Tc + tt));
+                nib = fadd(__ldg(a.ib + (int64_t)in * Tc + a.temp_num), __ldg(a.ib + (int64_t)in * Tc + tt));
+            }
         }
         const float* ur = a.U + (int64_t)iu * a.d;
         const float* pr = a.I + (int64_t)ip * a.d;
@@ -180,6 +191,8 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
             x = fsub(fmul(elu_p1(sp), pp), fmul(elu_p1(sn), pn));
             dp = fmul(elu_p1_grad(sp), pp);
             dn = fmul(elu_p1_grad(sn), pn);
+        } else if (TEMP) {
+            x = fsub(fadd(fmul(ubf, pib), sp), fadd(fmul(ubf, nib), sn)); dp = 1.0f; dn = 1.0f;
         } else {
             x = fsub(sp, sn); dp = 1.0f; dn = 1.0f;
         }
@@ -191,6 +204,13 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
         if (valid) {
             sq_acc += (double)sq;
             if (gl == 0) mf_acc += (double)logf(sige);
+            if (TEMP && gl == 0) {   // bias gradients: d/d ub[u,0] (t == 0 only), d/d ib[.,T] and d/d ib[.,t]
+                const int Tc = a.temp_num + 1;
+                if (tt == 0) atomicAdd(a.Gub + iu, fmul(cp, fsub(pib, nib)));
+                const float gpb = fmul(cp, ubf), gnb = fmul(cn, ubf);
+                atomicAdd(a.Gib + (int64_t)ip * Tc + a.temp_num, gpb); atomicAdd(a.Gib + (int64_t)ip * Tc + tt, gpb);
+                atomicAdd(a.Gib + (int64_t)in * Tc + a.temp_num, gnb); atomicAdd(a.Gib + (int64_t)in * Tc + tt, gnb);
+            }
             float* gu = a.GU + (int64_t)iu * a.d;
             float* gp = a.GI + (int64_t)ip * a.d;
             float* gn = a.GI + (int64_t)in * a.d;
@@ -233,12 +253,15 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
 
 template <int G, int C>
 static void launch_step_gc(const StepArgs& a, int grid, cudaStream_t st) {
-    if (a.pop_mode) {
-        if (a.uniq_users) bpr_step_kernel<G, C, true, true><<<grid, 256, 0, st>>>(a);
-        else bpr_step_kernel<G, C, true, false><<<grid, 256, 0, st>>>(a);
+    if (a.pop_mode == 1) {
+        if (a.uniq_users) bpr_step_kernel<G, C, 1, true><<<grid, 256, 0, st>>>(a);
+        else bpr_step_kernel<G, C, 1, false><<<grid, 256, 0, st>>>(a);
+    } else if (a.pop_mode == 2) {
+        if (a.uniq_users) bpr_step_kernel<G, C, 2, true><<<grid, 256, 0, st>>>(a);
+        else bpr_step_kernel<G, C, 2, false><<<grid, 256, 0, st>>>(a);
     } else {
-        if (a.uniq_users) bpr_step_kernel<G, C, false, true><<<grid, 256, 0, st>>>(a);
-        else bpr_step_kernel<G, C, false, false><<<grid, 256, 0, st>>>(a);
+        if (a.uniq_users) bpr_step_kernel<G, C, 0, true><<<grid, 256, 0, st>>>(a);
+        else bpr_step_kernel<G, C, 0, false><<<grid, 256, 0, st>>>(a);
     }
 }
 
@@ -288,14 +311,14 @@ __device__ __forceinline__ float adam_elem(float& w, float& m, float& v, float g
 __global__ void __launch_bounds__(256) adam_dense_kernel(AdamArgs a) {
     const float b1p = a.pw[0], b2p = a.pw[1];
     const float lr_t = fdiv(fmul(a.lr, fsqrt(fsub(1.0f, b2p))), fsub(1.0f, b1p));
-    const int64_t n4 = a.n4[0] + a.n4[1];
+    const int64_t e1 = a.n4[0], e2 = e1 + a.n4[1], e3 = e2 + a.n4[2], n4 = e3 + a.n4[3];
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
-        const bool t = e >= a.n4[0];
-        const int64_t k = t ? e - a.n4[0] : e;
-        float4* W = reinterpret_cast<float4*>(t ? a.W[1] : a.W[0]) + k;
-        float4* M = reinterpret_cast<float4*>(t ? a.m[1] : a.m[0]) + k;
-        float4* V = reinterpret_cast<float4*>(t ? a.v[1] : a.v[0]) + k;
-        float4* Gp = reinterpret_cast<float4*>(t ? a.G[1] : a.G[0]) + k;
+        const int t = e < e1 ? 0 : e < e2 ? 1 : e < e3 ? 2 : 3;
+        const int64_t k = e - (t == 0 ? 0 : t == 1 ? e1 : t == 2 ? e2 : e3);
+        float4* W = reinterpret_cast<float4*>(a.W[t]) + k;
+        float4* M = reinterpret_cast<float4*>(a.m[t]) + k;
+        float4* V = reinterpret_cast<float4*>(a.v[t]) + k;
+        float4* Gp = reinterpret_cast<float4*>(a.G[t]) + k;
         float4 w = *W, m = *M, v = *V, g = *Gp;
         adam_elem(w.x, m.x, v.x, g.x, lr_t);
         adam_elem(w.y, m.y, v.y, g.y, lr_t);
@@ -307,7 +330,7 @@ __global__ void __launch_bounds__(256) adam_dense_kernel(AdamArgs a) {
 }
 
 void launch_adam_dense(const AdamArgs& a, cudaStream_t st) {
-    int64_t n4 = a.n4[0] + a.n4[1];
+    int64_t n4 = a.n4[0] + a.n4[1] + a.n4[2] + a.n4[3];
     int64_t blocks = (n4 + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
@@ -315,20 +338,57 @@ void launch_adam_dense(const AdamArgs& a, cudaStream_t st) {
 }
 
 // loss3 = {loss, mf, reg}; beta powers advance (AdamOptimizer._finish); accumulators reset.
-__global__ void finish_step_kernel(double* loss_acc, float* loss3, float* pw, double B, double regs, double batch_size,
-                                   int advance_powers) {
+// stage labels arrive as fp32 in the pos_pop slot (tf.cast(temp, tf.int32), train_new_api.py:565); clamped to
+// [0, max_value] so a bad label can never index outside item_temp_init_bias
+__global__ void f32_to_i32_kernel(const float* __restrict__ src, int32_t* __restrict__ dst, int64_t n, int32_t max_value) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int32_t v = (int32_t)src[i];
+        dst[i] = v < 0 ? 0 : v > max_value ? max_value : v;
+    }
+}
+
+void launch_f32_to_i32(const float* src, int32_t* dst, int64_t n, int32_t max_value, cudaStream_t st) {
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    f32_to_i32_kernel<<<(int)blocks, 256, 0, st>>>(src, dst, n, max_value);
+}
+
+// BPR(t)-pop inference bias (model_api.py:373-387): (1 + ub[first user of the batch]) * (ib[:,T-1] + ib[:,T])
+__global__ void temp_item_bias_kernel(const float* __restrict__ ub, const float* __restrict__ ib, int64_t n_items,
+                                      int temp_num, int32_t first_user, float* __restrict__ out) {
+    const float f = fadd(ub[first_user], 1.0f);
+    const int Tc = temp_num + 1;
+    for (int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; j < n_items; j += (int64_t)gridDim.x * blockDim.x)
+        out[j] = fmul(f, fadd(ib[j * Tc + temp_num - 1], ib[j * Tc + temp_num]));
+}
+
+void launch_temp_item_bias(const float* ub, const float* ib, int64_t n_items, int temp_num, int32_t first_user,
+                           float* out, cudaStream_t st) {
+    int64_t blocks = (n_items + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    temp_item_bias_kernel<<<(int)blocks, 256, 0, st>>>(ub, ib, n_items, temp_num, first_user, out);
+}
+
+// loss_sum[0..2] accumulate the fp32 step losses in double (the epoch means of train_new_api.py:1095-1097),
+// loss_sum[3] counts the steps.
+__global__ void finish_step_kernel(double* loss_acc, float* loss3, double* loss_sum, float* pw, double B, double regs,
+                                   double batch_size, int advance_powers) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double mf = -loss_acc[0] / B;
         double reg = regs * 0.5 * loss_acc[1] / batch_size;
         loss3[0] = (float)(mf + reg); loss3[1] = (float)mf; loss3[2] = (float)reg;
+        loss_sum[0] += (double)loss3[0]; loss_sum[1] += (double)loss3[1]; loss_sum[2] += (double)loss3[2];
+        loss_sum[3] += 1.0;
         loss_acc[0] = 0.0; loss_acc[1] = 0.0;
         if (advance_powers) { pw[0] = fmul(pw[0], 0.9f); pw[1] = fmul(pw[1], 0.999f); }
     }
 }
 
-void launch_finish_step(double* loss_acc, float* loss3, float* pw, int64_t B, float regs, int batch_size,
-                        int advance_powers, cudaStream_t st) {
-    finish_step_kernel<<<1, 32, 0, st>>>(loss_acc, loss3, pw, (double)B, (double)regs, (double)batch_size, advance_powers);
+void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float* pw, int64_t B, float regs,
+                        int batch_size, int advance_powers, cudaStream_t st) {
+    finish_step_kernel<<<1, 32, 0, st>>>(loss_acc, loss3, loss_sum, pw, (double)B, (double)regs, (double)batch_size,
+                                         advance_powers);
 }
 
 }  // namespace pda

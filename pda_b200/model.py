@@ -16,7 +16,7 @@ import numpy as np
 from . import _lib
 from ._lib import PdaConfig, PdaError, check, ptr
 
-TRAIN_MODES = {"normal": 0, "s_condition": 1, "condition": 1}
+TRAIN_MODES = {"normal": 0, "s_condition": 1, "condition": 1, "temp_pop": 2}
 REC_TYPES = {"main_branch": 0, "main_with_pop": 1, "condition": 1}
 BACKENDS = {"auto": 0, "exact": 1, "tensor": 2}
 TOPK_MAX = 50  # Create_Recommendation(topk_max=50), train_new_api.py:594
@@ -34,15 +34,16 @@ class PDAModel:
     """One model on one GPU: embedding tables + TF1-Adam state + train CSR, owned by the library."""
 
     def __init__(self, n_users, n_items, embed_size=64, train="s_condition", batch_size=2048, lr=1e-3, regs=1e-5,
-                 device=0, max_batch=0, seed=2021, init=True):
+                 device=0, max_batch=0, seed=2021, init=True, temp_num=0):
         if train not in TRAIN_MODES:
             raise NotImplementedError("not implement this model: " + str(train))
         self.lib = _lib.load()
         self.n_users, self.n_items, self.emb_dim = int(n_users), int(n_items), int(embed_size)
         self.train, self.batch_size, self.lr, self.regs = train, int(batch_size), float(lr), float(regs)
         self.device = int(device)
+        self.temp_num = int(temp_num)
         cfg = PdaConfig(self.device, self.n_users, self.n_items, self.emb_dim, TRAIN_MODES[train], self.batch_size,
-                        self.lr, self.regs, int(max_batch))
+                        self.lr, self.regs, int(max_batch), self.temp_num)
         h = C.c_void_p()
         check(self.lib.pda_create(C.byref(cfg), C.byref(h)))
         self._h = h
@@ -84,20 +85,32 @@ class PDAModel:
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROF_KINDS)}
 
     # ---- state access (checkpoint interop: parameter/user_embedding, parameter/item_embedding) ----
-    _TABLES = {"user_embedding": 0, "item_embedding": 1, "user_m": 2, "user_v": 3, "item_m": 4, "item_v": 5}
+    _TABLES = {"user_embedding": 0, "item_embedding": 1, "user_m": 2, "user_v": 3, "item_m": 4, "item_v": 5,
+               "user_temp_bias": 6, "item_temp_bias": 7, "user_temp_bias_m": 8, "user_temp_bias_v": 9,
+               "item_temp_bias_m": 10, "item_temp_bias_v": 11}
+
+    def _shape(self, name):
+        k = self._TABLES[name]
+        if k in (0, 2, 3):
+            return (self.n_users, self.emb_dim)
+        if k in (1, 4, 5):
+            return (self.n_items, self.emb_dim)
+        if self.train != "temp_pop":
+            raise KeyError(name + " exists only for --train temp_pop")
+        return (self.n_users, 1) if k in (6, 8, 9) else (self.n_items, self.temp_num + 1)
 
     def _rows(self, name):
-        return self.n_users if self._TABLES[name] in (0, 2, 3) else self.n_items
+        return self._shape(name)[0]
 
     def get_table(self, name):
-        out = np.empty((self._rows(name), self.emb_dim), dtype=np.float32)
+        out = np.empty(self._shape(name), dtype=np.float32)
         check(self.lib.pda_get_table(self._h, self._TABLES[name], ptr(out)))
         return out
 
     def set_table(self, name, value):
         v = _f32(value)
-        if v.shape != (self._rows(name), self.emb_dim):
-            raise ValueError(f"{name}: expected {(self._rows(name), self.emb_dim)}, got {v.shape}")
+        if v.shape != self._shape(name):
+            raise ValueError(f"{name}: expected {self._shape(name)}, got {v.shape}")
         check(self.lib.pda_set_table(self._h, self._TABLES[name], ptr(v)))
 
     def table_ptr(self, name) -> int:
@@ -112,17 +125,28 @@ class PDAModel:
         v = np.array([b1p, b2p], dtype=np.float32)
         check(self.lib.pda_set_adam_powers(self._h, ptr(v)))
 
+    def _var_names(self):
+        # TF variable names of the reference (model_api.py:91-92, 397-400: the item bias variable is *named* item_temp_bias)
+        v = ["user_embedding", "item_embedding"]
+        return v + ["user_temp_bias", "item_temp_bias"] if self.train == "temp_pop" else v
+
+    def _slot_names(self):
+        s = ["user_m", "user_v", "item_m", "item_v"]
+        if self.train == "temp_pop":
+            s += ["user_temp_bias_m", "user_temp_bias_v", "item_temp_bias_m", "item_temp_bias_v"]
+        return s
+
     def state_dict(self):
-        d = {"parameter/" + k: self.get_table(k) for k in ("user_embedding", "item_embedding")}
-        for k in ("user_m", "user_v", "item_m", "item_v"):
+        d = {"parameter/" + k: self.get_table(k) for k in self._var_names()}
+        for k in self._slot_names():
             d["adam/" + k] = self.get_table(k)
         d["adam/beta_powers"] = self.get_adam_powers()
         return d
 
     def load_state_dict(self, d):
-        self.set_table("user_embedding", d["parameter/user_embedding"])
-        self.set_table("item_embedding", d["parameter/item_embedding"])
-        for k in ("user_m", "user_v", "item_m", "item_v"):
+        for k in self._var_names():
+            self.set_table(k, d["parameter/" + k])
+        for k in self._slot_names():
             if "adam/" + k in d:
                 self.set_table(k, d["adam/" + k])
         if "adam/beta_powers" in d:
@@ -170,7 +194,8 @@ class PDAModel:
     # ---- training ----
     def train_step(self, users, pos_items, neg_items, pos_pop=None, neg_pop=None):
         """One optimisation step on a host batch; returns (loss, mf_loss, reg_loss) like
-        sess.run([opt, loss, mf_loss, reg_loss])[1:]."""
+        sess.run([opt, loss, mf_loss, reg_loss])[1:].  For --train temp_pop the fourth array is the stage `temp`
+        of each triple (the slot the reference's iterator uses for it) and the fifth (`raw`) is optional."""
         u, p, n = _i32(users), _i32(pos_items), _i32(neg_items)
         pp = None if pos_pop is None else _f32(pos_pop)
         npop = None if neg_pop is None else _f32(neg_pop)
@@ -218,6 +243,12 @@ class PDAModel:
         check(self.lib.pda_read_loss(self._h, ptr(out), ptr(stream) if stream else None))
         return float(out[0]), float(out[1]), float(out[2])
 
+    def read_loss_sums(self, reset=True, stream=0):
+        """(sum loss, sum mf, sum reg, n_steps) accumulated on the device since the last reset."""
+        out = np.zeros(4, dtype=np.float64)
+        check(self.lib.pda_read_loss_sums(self._h, ptr(out), 1 if reset else 0, ptr(stream) if stream else None))
+        return out
+
     def gradients(self, users, pos_items, neg_items, pos_pop=None, neg_pop=None):
         u, p, n = _i32(users), _i32(pos_items), _i32(neg_items)
         pp = None if pos_pop is None else _f32(pos_pop)
@@ -228,6 +259,24 @@ class PDAModel:
         check(self.lib.pda_gradients_host(self._h, ptr(u), ptr(p), ptr(n), ptr(pp), ptr(npop), len(u), ptr(gU), ptr(gI),
                                           ptr(loss3)))
         return gU, gI, loss3
+
+    def gradients_temp(self, users, pos_items, neg_items, temp):
+        """BPR(t)-pop test hook: (gU, gI, g_user_temp_bias [n_users], g_item_temp_bias [n_items, T+1], loss3)."""
+        u, p, n, t = _i32(users), _i32(pos_items), _i32(neg_items), _f32(temp)
+        gU = np.empty((self.n_users, self.emb_dim), dtype=np.float32)
+        gI = np.empty((self.n_items, self.emb_dim), dtype=np.float32)
+        gub = np.empty(self.n_users, dtype=np.float32)
+        gib = np.empty((self.n_items, self.temp_num + 1), dtype=np.float32)
+        loss3 = np.zeros(3, dtype=np.float32)
+        check(self.lib.pda_gradients_temp_host(self._h, ptr(u), ptr(p), ptr(n), ptr(t), len(u), ptr(gU), ptr(gI), ptr(gub),
+                                               ptr(gib), ptr(loss3)))
+        return gU, gI, gub, gib, loss3
+
+    def temp_item_bias_for_eval(self, first_user):
+        """model_api.py:373-387: (1 + user_temp_bias[first user of the batch]) * (item_bias[:, T-1] + item_bias[:, T])."""
+        out = np.empty(self.n_items, dtype=np.float32)
+        check(self.lib.pda_temp_item_bias_host(self._h, int(first_user), ptr(out)))
+        return out
 
     # ---- inference (DatasetApi_Model) ----
     def do_recommendation(self, batch_users, items=None, rec_type="main_branch", pos_pop=None, sparse_cliked_matrix=None,

@@ -68,10 +68,10 @@ def test_exported_symbols_are_plain_c(lib):
 def test_config_struct_layout_matches_header():
     from pda_b200._lib import PdaConfig
     # device i32 | pad | n_users i64 | n_items i64 | embed_size i32 | train_mode i32 | batch_size i32 | lr f32 |
-    # regs f32 | pad | max_batch i64   (natural alignment of the C struct in include/pda_b200.h)
+    # regs f32 | pad | max_batch i64 | temp_num i32 | pad   (natural alignment of the C struct in include/pda_b200.h)
     assert PdaConfig.n_users.offset == 8 and PdaConfig.n_items.offset == 16 and PdaConfig.embed_size.offset == 24
     assert PdaConfig.lr.offset == 36 and PdaConfig.regs.offset == 40 and PdaConfig.max_batch.offset == 48
-    assert C.sizeof(PdaConfig) == 56
+    assert PdaConfig.temp_num.offset == 56 and C.sizeof(PdaConfig) == 64
 
 
 def test_version_and_error_string(lib):
@@ -85,7 +85,7 @@ def test_no_cpu_fallback_without_a_gpu(lib):
         pytest.skip("a GPU is visible: the loud-failure path is not reachable")
     import pda_b200
     from pda_b200._lib import PdaConfig
-    cfg = PdaConfig(0, 10, 10, 8, 0, 4, 1e-3, 1e-5, 0)
+    cfg = PdaConfig(0, 10, 10, 8, 0, 4, 1e-3, 1e-5, 0, 0)
     h = C.c_void_p()
     rc = lib.pda_create(C.byref(cfg), C.byref(h))
     assert rc == 2 and not h.value
@@ -97,9 +97,10 @@ def test_no_cpu_fallback_without_a_gpu(lib):
 def test_argument_validation_happens_before_cuda(lib):
     from pda_b200._lib import PdaConfig
     h = C.c_void_p()
-    for bad in (PdaConfig(0, 10, 10, 7, 0, 4, 1e-3, 1e-5, 0),      # embed_size % 4
-                PdaConfig(0, 0, 10, 8, 0, 4, 1e-3, 1e-5, 0),       # n_users < 1
-                PdaConfig(0, 10, 10, 8, 9, 4, 1e-3, 1e-5, 0)):     # unknown train_mode
+    for bad in (PdaConfig(0, 10, 10, 7, 0, 4, 1e-3, 1e-5, 0, 0),      # embed_size % 4
+                PdaConfig(0, 0, 10, 8, 0, 4, 1e-3, 1e-5, 0, 0),       # n_users < 1
+                PdaConfig(0, 10, 10, 8, 9, 4, 1e-3, 1e-5, 0, 0),     # unknown train_mode
+                PdaConfig(0, 10, 10, 8, 2, 4, 1e-3, 1e-5, 0, 0)):    # temp_pop without temp_num
         assert lib.pda_create(C.byref(bad), C.byref(h)) == 1       # PDA_ERR_ARG
         assert lib.pda_last_error()
     assert lib.pda_create(None, C.byref(h)) == 1
