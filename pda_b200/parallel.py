@@ -39,10 +39,13 @@ class ShardedTrainer:
             import torch.distributed as dist
             if reducer is None:
                 self._reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            dev = torch.device("cuda", model.device)
-            self._gi = torch.as_tensor(_DevArray(model.grad_ptr("item_embedding"), (model.n_items, model.emb_dim), "<f4"),
-                                       device=dev)
-            self._acc = torch.as_tensor(_DevArray(model.loss_acc_ptr(), (2,), "<f8"), device=dev)
+            if hasattr(model, "exchange_tensors"):     # host stand-ins (tests) hand their buffers over directly
+                self._gi, self._acc = model.exchange_tensors()
+            else:
+                dev = torch.device("cuda", model.device)
+                self._gi = torch.as_tensor(_DevArray(model.grad_ptr("item_embedding"), (model.n_items, model.emb_dim),
+                                                     "<f4"), device=dev)
+                self._acc = torch.as_tensor(_DevArray(model.loss_acc_ptr(), (2,), "<f8"), device=dev)
 
     def _exchange(self):
         self._reduce(self._gi)     # dense item-gradient block, summed over ranks (NVLink / NVSwitch)
