@@ -188,6 +188,10 @@ int pda_recommend_host(pda_model* m, const int32_t* users, int64_t M, int rec_ty
 int pda_recommend_device(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop,
                          const float* col_bias, int use_mask, int K, int backend, int32_t* ids_out, float* scores_out,
                          void* stream);
+/* diagnostics of the last tensor-core eval block: out[8] = {rows, rows recomputed by the exact kernel (no certificate),
+ * candidates rescored, max candidates of a row, rows whose candidate list overflowed, pass-A tile stride, sampled
+ * chunks per row, item-range splits}.  Synchronises the device. */
+int pda_tc_last_stats(pda_model* m, int64_t* out);
 /* dense scores -- replaces testing()/predict() (train_new_api.py:642-696): out fp32 [M, n_items], no mask */
 int pda_scores_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop, float* out);
 

@@ -56,6 +56,8 @@ struct pda_model {
     void* stage_pinned; size_t stage_bytes;
     // eval scratch
     void* ev_buf; size_t ev_bytes;
+    void* tc_buf; size_t tc_bytes;   // scratch of the tensor-core filter
+    TcPlan tc_last_plan; int64_t tc_last_M;
     float* grad_bias_out[2];   // pda_gradients_temp_host: host destinations of the bias gradients
     void* ev_pinned; size_t ev_pinned_bytes;
     // optional per-kernel CUDA-event timing (pda_profile_*): [kernel kind][slot][begin/end]
@@ -175,6 +177,7 @@ void pda_destroy(pda_model* m) {
     cudaFree(m->b_users); cudaFree(m->b_pos); cudaFree(m->b_neg); cudaFree(m->b_time); cudaFree(m->b_pp); cudaFree(m->b_np);
     if (m->stage_pinned) cudaFreeHost(m->stage_pinned);
     if (m->ev_buf) cudaFree(m->ev_buf);
+    if (m->tc_buf) cudaFree(m->tc_buf);
     if (m->ev_pinned) cudaFreeHost(m->ev_pinned);
     if (m->prof_ev) {
         for (int k = 0; k < PDA_PROF_KINDS; ++k)
@@ -673,10 +676,39 @@ int pda_temp_item_bias_host(pda_model* m, int32_t first_user, float* out) {
 }
 
 // ---- recommendation ----
+// PDA_EVAL_AUTO: the tcgen05 filter when the shape supports it (d in {64,128}, >= 4096 items) and there are enough
+// rows to fill the machine, else the exact CUDA-core kernel.  Both give identical ids and scores.
 static int do_recommend(pda_model* m, const EvalArgs& a, int backend, cudaStream_t st) {
-    if (backend == PDA_EVAL_TENSOR) return fail(PDA_ERR_ARG, "tensor-core eval back end is not built into this library yet");
-    ProfScope ps(m, PDA_PROF_EVAL, st);
-    if (launch_recommend_exact(a, st)) return fail(PDA_ERR_ARG, "bad eval arguments (K in [1,128], M >= 1)");
+    if (a.K < 1 || a.K > 128 || a.M < 1) return fail(PDA_ERR_ARG, "bad eval arguments (K in [1,128], M >= 1)");
+    const bool tc_ok = tc_supported(a);
+    if (backend == PDA_EVAL_TENSOR && !tc_ok)
+        return fail(PDA_ERR_ARG, "tensor-core eval needs embed_size in {64,128}, n_items >= 4096 (got d=%d, n_items=%lld)", a.d,
+                    (long long)a.N);
+    const bool use_tc = backend == PDA_EVAL_TENSOR || (backend == PDA_EVAL_AUTO && tc_ok && a.M >= 512);
+    if (!use_tc) {
+        ProfScope ps(m, PDA_PROF_EVAL, st);
+        if (launch_recommend_exact(a, st)) return fail(PDA_ERR_ARG, "bad eval arguments (K in [1,128], M >= 1)");
+        return PDA_OK;
+    }
+    // user blocks bound the scratch (chunk maxima + candidate lists are per row)
+    const int64_t MB = 32768;
+    EvalArgs blk = a;
+    blk.M = a.M < MB ? a.M : MB;
+    TcPlan plan;
+    const size_t need = tc_scratch_bytes(blk, &plan);
+    CK(ensure_dev(&m->tc_buf, &m->tc_bytes, need));
+    for (int64_t m0 = 0; m0 < a.M; m0 += MB) {
+        blk = a;
+        blk.users = a.users + m0;
+        blk.M = a.M - m0 < MB ? a.M - m0 : MB;
+        blk.ids_out = a.ids_out + m0 * a.K;
+        blk.scores_out = a.scores_out ? a.scores_out + m0 * a.K : nullptr;
+        tc_scratch_bytes(blk, &plan);
+        m->tc_last_plan = plan; m->tc_last_M = blk.M;
+        ProfScope ps(m, PDA_PROF_EVAL_TC, st);
+        const int rc = launch_recommend_tc(blk, m->tc_buf, plan, st);
+        if (rc) return fail(PDA_ERR_CUDA, "tensor-core eval launch failed (stage %d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+    }
     return PDA_OK;
 }
 
@@ -720,6 +752,29 @@ int pda_recommend_host(pda_model* m, const int32_t* users, int64_t M, int rec_ty
     if (scores_out) CK(cudaMemcpyAsync(scores_out, d_sc, (size_t)M * K * 4, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));
     CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+int pda_tc_last_stats(pda_model* m, int64_t* out) {
+    if (!m || !out) return fail(PDA_ERR_ARG, "null argument");
+    if (!m->tc_buf || m->tc_last_M < 1) return fail(PDA_ERR_STATE, "the tensor-core eval path has not run yet");
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaDeviceSynchronize());
+    const TcPlan& p = m->tc_last_plan;
+    const int64_t M = m->tc_last_M;
+    int32_t nflag = 0;
+    CK(cudaMemcpy(&nflag, (char*)m->tc_buf + p.o_nflag, 4, cudaMemcpyDeviceToHost));
+    int32_t* cnt = (int32_t*)malloc((size_t)M * 4);
+    if (!cnt) return fail(PDA_ERR_STATE, "out of host memory");
+    CK(cudaMemcpy(cnt, (char*)m->tc_buf + p.o_cnt, (size_t)M * 4, cudaMemcpyDeviceToHost));
+    int64_t tot = 0, mx = 0, over = 0;
+    for (int64_t r = 0; r < M; ++r) {
+        tot += cnt[r] < p.cap ? cnt[r] : p.cap;
+        if (cnt[r] > mx) mx = cnt[r];
+        if (cnt[r] > p.cap) ++over;
+    }
+    free(cnt);
+    out[0] = M; out[1] = nflag; out[2] = tot; out[3] = mx; out[4] = over; out[5] = p.se; out[6] = p.n_c; out[7] = p.splits;
     return PDA_OK;
 }
 

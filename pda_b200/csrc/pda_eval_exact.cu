@@ -66,10 +66,12 @@ __global__ void __launch_bounds__(E_NT, 2) recommend_exact_kernel(EvalArgs a, in
     const int ty = tid >> 4, tx = tid & 15;
     const int64_t m0 = (int64_t)blockIdx.x * E_TM;
     const int K = a.K, d = a.d;
+    const int64_t Meff = a.M_dev ? (int64_t)*a.M_dev : a.M;    // device-sized launch (tensor path fallback rows)
+    if (m0 >= Meff) return;
 
     for (int r = tid; r < E_TM; r += E_NT) {
         const int64_t m = m0 + r;
-        const int u = m < a.M ? a.users[m] : -1;
+        const int u = m < Meff ? a.users[m] : -1;
         urow[r] = u;
         mcur[r] = (u >= 0 && a.mask_indptr) ? a.mask_indptr[u] : 0;
     }
@@ -180,10 +182,11 @@ __global__ void __launch_bounds__(E_NT, 2) recommend_exact_kernel(EvalArgs a, in
     for (int e = tid; e < E_TM * K; e += E_NT) {
         const int r = e / K, k = e - r * K;
         const int64_t m = m0 + r;
-        if (m < a.M) {
+        if (m < Meff) {
+            const int64_t mo = a.out_rows ? (int64_t)a.out_rows[m] : m;
             const int idv = tid_[r * Kp + k];
-            if (a.ids_out) a.ids_out[m * K + k] = idv == 0x7fffffff ? -1 : idv;
-            if (a.scores_out) a.scores_out[m * K + k] = tval[r * Kp + k];
+            if (a.ids_out) a.ids_out[mo * K + k] = idv == 0x7fffffff ? -1 : idv;
+            if (a.scores_out) a.scores_out[mo * K + k] = tval[r * Kp + k];
         }
     }
 }

@@ -49,6 +49,15 @@ struct EvalArgs {
     int K;
     int32_t* ids_out; float* scores_out;    // [M,K]
     float* dense_out;                       // optional [M,N] transformed scores (unmasked)
+    const int32_t* M_dev;                   // optional device-side row count (<= M): CTAs beyond it exit at once
+    const int32_t* out_rows;                // optional [M] output row of each input row (scatter of fallback rows)
+};
+
+// plan + scratch layout of the tensor-core filter (pda_eval_tc.cu)
+struct TcPlan {
+    int64_t M_pad, N_pad;
+    int n_tiles, se, n_c, cap, splits, tiles_per_split;
+    size_t o_Ib, o_Ub, o_inorm, o_unorm, o_tnorm, o_cmax, o_tau, o_cnt, o_cand, o_flag, o_frows, o_fusers, o_nflag;
 };
 
 void launch_xavier_init(float* W, int64_t rows, int cols, uint32_t seed, uint32_t table_id, cudaStream_t st);
@@ -62,6 +71,9 @@ void launch_f32_to_i32(const float* src, int32_t* dst, int64_t n, int32_t max_va
 void launch_temp_item_bias(const float* ub, const float* ib, int64_t n_items, int temp_num, int32_t first_user,
                            float* out, cudaStream_t st);
 int launch_recommend_exact(const EvalArgs& a, cudaStream_t st);
+bool tc_supported(const EvalArgs& a);
+size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* plan);
+int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& plan, cudaStream_t st);
 void launch_metrics(const int32_t* ids, int64_t M, int Kkeep, const int32_t* eval_users, const int64_t* truth_indptr,
                     const int32_t* truth_items, const int32_t* Ks, int nK, double* out, cudaStream_t st);
 

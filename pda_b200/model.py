@@ -303,6 +303,12 @@ class PDAModel:
                                           1 if (mask and self._has_csr) else 0, K, BACKENDS[backend], ptr(ids), ptr(sc)))
         return (ids, sc) if return_scores else ids
 
+    def tc_last_stats(self):
+        out = np.zeros(8, dtype=np.int64)
+        check(self.lib.pda_tc_last_stats(self._h, ptr(out)))
+        return dict(zip(("rows", "rows_exact_fallback", "candidates", "max_candidates_row", "rows_overflow", "tile_stride",
+                         "sampled_chunks", "item_splits"), (int(x) for x in out)))
+
     def testing(self, batch_users, items=None, model_type="main_branch", pos_pop=None):
         """train_new_api.py:642-669: dense fp32 [len(batch_users), n_items] ratings (no mask)."""
         if model_type not in ("main_branch", "condition"):

@@ -90,3 +90,57 @@ def test_metrics_match_oracle(pda, c_oracle):
     for k in want:
         assert np.allclose(got[k], want[k], rtol=1e-12, atol=1e-12), k
     m.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 filter + exact rescoring: must return exactly what the exact kernel / the oracle return
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_users,n_items,d,K", [(700, 5000, 64, 50), (300, 9000, 128, 50), (1000, 4096, 64, 20),
+                                                 (130, 20000, 64, 100)])
+@pytest.mark.parametrize("rec_type", ["main_branch", "condition"])
+def test_recommend_tensor_matches_oracle(pda, c_oracle, n_users, n_items, d, K, rec_type):
+    m, U, I, indptr, items, pop, rng = _setup(pda, n_users, n_items, d, seed=n_items + d, scale=3.0)
+    users = rng.permutation(n_users)[: n_users - 3].astype(np.int32)
+    ids, sc = m.do_recommendation(users, None, rec_type, pos_pop=pop, K=K, backend="tensor", return_scores=True)
+    st = m.tc_last_stats()
+    rid, rsc = c_oracle.recommend(U, I, users, rec_type, K, indptr, items, pop=pop)
+    assert np.array_equal(ids, rid), st
+    assert np.array_equal(bits(sc), bits(rsc))
+    # the filter must actually carry the load: few rows may need the exact kernel, candidate lists stay short
+    assert st["rows"] == len(users) and st["rows_exact_fallback"] <= 0.05 * len(users), st
+    assert st["candidates"] <= 40 * K * len(users), st
+    m.close()
+
+
+def test_recommend_tensor_heavy_masks_and_bias(pda, c_oracle):
+    """rows whose best items are all train items (the mask removes the top of the ranking) and the BPR(t)-pop bias."""
+    from oracle import pda_oracle as po
+    rng = np.random.default_rng(21)
+    n_users, n_items, d, K = 600, 6000, 64, 50
+    U = (rng.normal(0, 1.0, (n_users, d)) / np.sqrt(d)).astype(np.float32)
+    I = (rng.normal(0, 1.0, (n_items, d)) / np.sqrt(d)).astype(np.float32)
+    S = U @ I.T
+    # train items = each user's own top-300 scored items (what a fitted model looks like), some users: none
+    top = np.argsort(-S, axis=1)[:, :300]
+    uid = np.repeat(np.arange(n_users), 300)[: 300 * (n_users - 50)]
+    iid = top[: n_users - 50].reshape(-1)
+    indptr, items, _ = po.build_csr(n_users, uid, iid)
+    bias = rng.normal(0, 0.05, n_items).astype(np.float32)
+    m = pda.PDAModel(n_users, n_items, d, train="normal", batch_size=64, init=False)
+    m.set_table("user_embedding", U); m.set_table("item_embedding", I)
+    m.set_train_csr(indptr, items)
+    users = np.arange(n_users, dtype=np.int32)
+    for cb in (None, bias):
+        ids, sc = m.do_recommendation(users, None, "main_branch", K=K, col_bias=cb, backend="tensor", return_scores=True)
+        rid, rsc = c_oracle.recommend(U, I, users, "main_branch", K, indptr, items, col_bias=cb)
+        assert np.array_equal(ids, rid) and np.array_equal(bits(sc), bits(rsc)), m.tc_last_stats()
+    m.close()
+
+
+def test_tensor_backend_rejects_unsupported_shapes(pda):
+    m = pda.PDAModel(100, 5000, 32, train="normal", batch_size=8)
+    with pytest.raises(pda.PdaError, match="tensor-core eval needs"):
+        m.do_recommendation(np.arange(10, dtype=np.int32), None, "main_branch", K=10, backend="tensor")
+    ids = m.do_recommendation(np.arange(10, dtype=np.int32), None, "main_branch", K=10, backend="auto")   # exact kernel
+    assert ids.shape == (10, 10)
+    m.close()
