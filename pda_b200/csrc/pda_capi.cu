@@ -764,14 +764,20 @@ int pda_tc_last_stats(pda_model* m, int64_t* out) {
     const int64_t M = m->tc_last_M;
     int32_t nflag = 0;
     CK(cudaMemcpy(&nflag, (char*)m->tc_buf + p.o_nflag, 4, cudaMemcpyDeviceToHost));
-    int32_t* cnt = (int32_t*)malloc((size_t)M * 4);
+    int32_t* cnt = (int32_t*)malloc((size_t)M * p.n_seg * 4);
     if (!cnt) return fail(PDA_ERR_STATE, "out of host memory");
-    CK(cudaMemcpy(cnt, (char*)m->tc_buf + p.o_cnt, (size_t)M * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cnt, (char*)m->tc_buf + p.o_cnt, (size_t)M * p.n_seg * 4, cudaMemcpyDeviceToHost));
     int64_t tot = 0, mx = 0, over = 0;
     for (int64_t r = 0; r < M; ++r) {
-        tot += cnt[r] < p.cap ? cnt[r] : p.cap;
-        if (cnt[r] > mx) mx = cnt[r];
-        if (cnt[r] > p.cap) ++over;
+        int64_t row_tot = 0; bool ov = false;
+        for (int sg = 0; sg < p.n_seg; ++sg) {
+            const int32_t c = cnt[r * p.n_seg + sg];
+            row_tot += c < p.seg_cap ? c : p.seg_cap;
+            if (c > p.seg_cap) ov = true;
+        }
+        tot += row_tot;
+        if (row_tot > mx) mx = row_tot;
+        if (ov) ++over;
     }
     free(cnt);
     out[0] = M; out[1] = nflag; out[2] = tot; out[3] = mx; out[4] = over; out[5] = p.se; out[6] = p.n_c; out[7] = p.splits;

@@ -174,7 +174,10 @@ struct SweepArgs {
     float* cmax;               // [n_c][M_pad]
     // pass B
     const float* tau;          // [M_pad]
-    int32_t* cand; int32_t* cnt; int cap;
+    int32_t* cand;             // [M_pad][n_seg][seg_cap] item ids, ascending inside a segment;
+                               // segment = (item split, column half): exactly one owner thread, no atomics
+    int32_t* cnt;              // [M_pad][n_seg] entries written (> seg_cap = overflow)
+    int n_seg, seg_cap;
 };
 
 template <int MODE, int PASS>
@@ -263,68 +266,129 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
         const int64_t row = (int64_t)m_tile * TM + 32 * q + lane;
         const bool row_ok = row < a.M;
         const float un = a.unorm[row] * a.c_err;
+        const bool use_col = MODE == 1 || a.col != nullptr;
         float tau = 0.f;
         if (PASS == 1) tau = row_ok ? a.tau[row] : INFINITY;
+        // pass B: this thread owns segment (split, h) of its row's candidate list -> no atomics
+        const int seg = blockIdx.y * 2 + h;
+        int32_t* my_cand = PASS == 1 ? a.cand + ((int64_t)row * a.n_seg + seg) * a.seg_cap : nullptr;
+        int n_local = 0;
+        const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * 128);
         for (int i = 0; i < n_my; ++i) {
             const int t = t_first + i * step;
             const int acc = i & 1, aph = (i >> 1) & 1;
             const int64_t j0 = (int64_t)t * TN;
-            float* sc = scol + acc * 256;
-            if (MODE == 1 || a.col) {
+            const float* sc = scol + acc * 256 + h * 128;
+            if (use_col) {
                 const int64_t j = j0 + e;
-                sc[e] = j < a.N ? __ldg(a.col + j) : 0.f;
+                scol[acc * 256 + e] = j < a.N ? __ldg(a.col + j) : 0.f;
                 asm volatile("bar.sync 1, 256;" ::: "memory");
             }
             const float er = un * __ldg(a.tile_inorm + t);       // |s - s_lp| <= er for every item of this tile
             mbar_wait(bar_tfull + 8 * acc, aph);
             fence_after();
-#pragma unroll 1
+            uint32_t va[32], vb[32];
+            const uint32_t tbase = lane_base + (uint32_t)(acc * TN);
+            tmem_ld32(tbase, va);
+#pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(acc * TN + h * 128 + cc * 32), v);
+                uint32_t* v = (cc & 1) ? vb : va;
                 tmem_ld_wait();
-                const int cb = h * 128 + cc * 32;                // first column of this chunk inside the tile
-                const int64_t jb = j0 + cb;
+                if (cc < 3) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), (cc & 1) ? va : vb);   // next chunk in flight
+                else {
+                    // all four chunks are in registers: hand the accumulator stage back to the MMA warp
+                    fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                }
+                const int cb = cc * 32;                          // first column of this chunk inside this thread's half
+                const int64_t jb = j0 + h * 128 + cb;
                 if (PASS == 0) {
                     float best = -INFINITY;
-                    const bool tail_chunk = jb + 32 > a.N;
+                    if (jb + 32 <= a.N) {
+                        if (MODE == 1) {
+                            // lower bound of (elu(s)+1)*pop: f(x) >= x + 1 (also when x + 1 < 0: the product then is <= 0 <= y)
+                            const float k1 = 1.0f - er;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float s = __uint_as_float(v[c]);
-                        float y;
-                        if (MODE == 1) y = fmaxf(s - er + 1.0f, 0.0f) * sc[cb + c];
-                        else y = a.col ? (s - er) + sc[cb + c] : s - er;
-                        y = __uint_as_float((__float_as_uint(y) & ~31u) | (uint32_t)c);
-                        if (tail_chunk && jb + c >= a.N) y = -INFINITY;
-                        best = fmaxf(best, y);
+                            for (int c = 0; c < 32; c += 4) {
+                                const float4 p4 = *reinterpret_cast<const float4*>(sc + cb + c);
+                                best = fmaxf(best, (__uint_as_float(v[c + 0]) + k1) * p4.x);
+                                best = fmaxf(best, (__uint_as_float(v[c + 1]) + k1) * p4.y);
+                                best = fmaxf(best, (__uint_as_float(v[c + 2]) + k1) * p4.z);
+                                best = fmaxf(best, (__uint_as_float(v[c + 3]) + k1) * p4.w);
+                            }
+                        } else if (use_col) {
+                            const float k1 = -er;
+#pragma unroll
+                            for (int c = 0; c < 32; c += 4) {
+                                const float4 p4 = *reinterpret_cast<const float4*>(sc + cb + c);
+                                best = fmaxf(best, (__uint_as_float(v[c + 0]) + k1) + p4.x);
+                                best = fmaxf(best, (__uint_as_float(v[c + 1]) + k1) + p4.y);
+                                best = fmaxf(best, (__uint_as_float(v[c + 2]) + k1) + p4.z);
+                                best = fmaxf(best, (__uint_as_float(v[c + 3]) + k1) + p4.w);
+                            }
+                        } else {
+                            // max first, bound after: s - er is monotone in s
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) best = fmaxf(best, __uint_as_float(v[c]));
+                            best -= er;
+                        }
+                    } else {
+                        // the last tile: padded columns (zero rows) must not produce a bound
+                        for (int c = 0; c < 32; ++c) {
+                            if (jb + c >= a.N) break;
+                            const float s = __uint_as_float(v[c]);
+                            float y;
+                            if (MODE == 1) y = (s + (1.0f - er)) * sc[cb + c];
+                            else y = use_col ? (s - er) + sc[cb + c] : s - er;
+                            best = fmaxf(best, y);
+                        }
                     }
                     const int sc_idx = (t / a.se) * 8 + h * 4 + cc;
                     a.cmax[(int64_t)sc_idx * a.M_pad + row] = best;
                 } else {
                     uint32_t hits = 0;
+                    if (MODE == 1) {
+                        // upper bound: f(x) <= max(x + 1, 1)
+                        const float k1 = 1.0f + er;
 #pragma unroll
-                    for (int c = 0; c < 32; ++c) {
-                        const float s = __uint_as_float(v[c]);
-                        float y;
-                        if (MODE == 1) y = fmaxf(s + er + 1.0f, 1.0f) * sc[cb + c];
-                        else y = a.col ? (s + er) + sc[cb + c] : s + er;
-                        hits |= (y >= tau) ? (1u << c) : 0u;
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 p4 = *reinterpret_cast<const float4*>(sc + cb + c);
+                            const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                            for (int z = 0; z < 4; ++z) {
+                                const float y = fmaxf(__uint_as_float(v[c + z]) + k1, 1.0f) * pc[z];
+                                if (y >= tau) hits |= 1u << (c + z);
+                            }
+                        }
+                    } else if (use_col) {
+#pragma unroll
+                        for (int c = 0; c < 32; c += 4) {
+                            const float4 p4 = *reinterpret_cast<const float4*>(sc + cb + c);
+                            const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                            for (int z = 0; z < 4; ++z)
+                                if ((__uint_as_float(v[c + z]) + er) + pc[z] >= tau) hits |= 1u << (c + z);
+                        }
+                    } else {
+                        const float thr = tau - er - fabsf(tau) * 4e-6f;      // s + er >= tau, rounding-safe
+#pragma unroll
+                        for (int c = 0; c < 32; ++c)
+                            if (__uint_as_float(v[c]) >= thr) hits |= 1u << c;
                     }
                     while (hits) {
                         const int c = __ffs(hits) - 1;
                         hits &= hits - 1;
                         const int64_t j = jb + c;
                         if (j < a.N) {
-                            const int pos = atomicAdd(a.cnt + row, 1);
-                            if (pos < a.cap) a.cand[row * a.cap + pos] = (int32_t)j;
+                            if (n_local < a.seg_cap) my_cand[n_local] = (int32_t)j;
+                            ++n_local;                               // > seg_cap marks the overflow
                         }
                     }
                 }
             }
-            fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
         }
+        if (PASS == 1) a.cnt[(int64_t)row * a.n_seg + seg] = n_local;
     }
     fence_before();
     __syncthreads();
@@ -348,151 +412,260 @@ __device__ __forceinline__ bool csr_row_contains(const int32_t* __restrict__ ite
 
 constexpr int TAU_MAX_KEYS = 2048;
 
+// K-th largest of n 32-bit keys in shared memory (one warp): 4-pass MSB radix select, 256-bin histogram per pass.
+// Returns the key value; *n_greater = number of keys strictly greater.  hist: 256 ints of per-warp shared memory.
+__device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t* keys, int n, int K, int* hist, int lane, int* n_greater) {
+    uint32_t prefix = 0, mask = 0;
+    int need = K, above = 0;
+    for (int pass = 3; pass >= 0; --pass) {
+        const int shift = pass * 8;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) hist[lane * 8 + b] = 0;
+        __syncwarp();
+        for (int c = lane; c < n; c += 32) {
+            const uint32_t k = keys[c];
+            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+        }
+        __syncwarp();
+        // lane L owns bins 255-8L .. 248-8L (descending); find the bin where the count from the top reaches `need`
+        int cntb[8], lsum = 0;
+#pragma unroll
+        for (int b = 0; b < 8; ++b) { cntb[b] = hist[255 - (lane * 8 + b)]; lsum += cntb[b]; }
+        int incl = lsum;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        const int excl = incl - lsum;
+        const unsigned bal = __ballot_sync(0xffffffffu, incl >= need);
+        const int owner = __ffs(bal) - 1;            // bal != 0 because need <= matching keys
+        int bin = 0, before = 0;
+        if (lane == owner) {
+            int run = excl;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (run + cntb[b] >= need) { bin = 255 - (lane * 8 + b); before = run; break; }
+                run += cntb[b];
+            }
+        }
+        bin = __shfl_sync(0xffffffffu, bin, owner);
+        before = __shfl_sync(0xffffffffu, before, owner);
+        above += before;
+        need -= before;
+        prefix |= (uint32_t)bin << shift;
+        mask |= 255u << shift;
+        __syncwarp();
+    }
+    *n_greater = above;
+    return prefix;
+}
+
+// one warp per row, n_c keys + 256 histogram bins per warp in dynamic shared memory
 __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restrict__ cmax, int n_c, int64_t M, int64_t M_pad,
                                                             int se, const int32_t* __restrict__ users,
                                                             const int64_t* __restrict__ mask_indptr,
                                                             const int32_t* __restrict__ mask_items, int K,
-                                                            float* __restrict__ tau, int32_t* __restrict__ cnt, int cap) {
-    __shared__ uint32_t keys[4][TAU_MAX_KEYS];
+                                                            float* __restrict__ tau) {
+    extern __shared__ uint32_t tau_keys[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 4 + w;
     if (row >= M_pad) return;
     if (row >= M) { if (lane == 0) tau[row] = INFINITY; return; }
-    const int u = users[row];
-    int64_t lo = 0, hi = 0;
-    if (mask_indptr) { lo = mask_indptr[u]; hi = mask_indptr[u + 1]; }
-    uint32_t* kk = keys[w];
+    uint32_t* kk = tau_keys + (size_t)w * (n_c + 256);
+    int* hist = reinterpret_cast<int*>(kk + n_c);
     for (int c = lane; c < n_c; c += 32) {
         const float v = cmax[(int64_t)c * M_pad + row];
-        uint32_t key = 0;   // below every real value
-        if (v > -INFINITY) {
-            // sampled chunk c = (sampled tile c/8, chunk c%8): item = ((c/8)*se*256) + (c%8)*32 + low 5 bits
-            const int32_t item = (int32_t)((int64_t)(c >> 3) * se * tc::TN + (c & 7) * 32 + (__float_as_uint(v) & 31u));
-            if (!(hi > lo && csr_row_contains(mask_items, lo, hi, item))) key = f2key(v);
-        }
-        kk[c] = key;
+        kk[c] = v > -INFINITY ? f2key(v) : 0u;    // 0 sorts below every real value
     }
     __syncwarp();
-    // K-th largest key by bisection on the bits
-    uint32_t prefix = 0;
-    for (int bit = 31; bit >= 0; --bit) {
-        const uint32_t cand = prefix | (1u << bit);
-        int cntge = 0;
-        for (int c = lane; c < n_c; c += 32) cntge += kk[c] >= cand;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) cntge += __shfl_xor_sync(0xffffffffu, cntge, off);
-        if (cntge >= K) prefix = cand;
-    }
-    if (lane == 0) {
-        if (prefix == 0) {
-            // fewer than K unmasked sampled maxima: no threshold -> hand the row to the exact kernel (overflow mark)
-            tau[row] = INFINITY;
-            cnt[row] = cap + 1;
-        } else {
-            // the packed column perturbs a value by < 2^-18 relative, the bound arithmetic by a few ulp: step down
-            const float t = key2f(prefix);
-            tau[row] = t - fabsf(t) * 1e-5f - 1e-30f;
+    // A sampled chunk that holds ANY train item of this user is dropped: its maximum may belong to a masked item.
+    // sampled chunk c = (sampled tile c/8, chunk c%8) covers items [(c/8)*se*256 + (c%8)*32, +32)
+    if (mask_indptr) {
+        const int u = users[row];
+        const int64_t lo = mask_indptr[u], hi = mask_indptr[u + 1];
+        for (int64_t z = lo + lane; z < hi; z += 32) {
+            const int32_t it = __ldg(mask_items + z);
+            const int tile = it / tc::TN;
+            if (tile % se == 0) {
+                const int c = (tile / se) * 8 + ((it % tc::TN) >> 5);
+                if (c < n_c) kk[c] = 0u;
+            }
         }
+        __syncwarp();
+    }
+    int n_clean = 0;
+    for (int c = lane; c < n_c; c += 32) n_clean += kk[c] != 0u;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) n_clean += __shfl_xor_sync(0xffffffffu, n_clean, off);
+    if (n_clean < K) {
+        if (lane == 0) tau[row] = INFINITY;     // fewer than K clean maxima: no candidates -> no certificate -> exact kernel
+        return;
+    }
+    int above;
+    const uint32_t kth = warp_kth_largest(kk, n_c, K, hist, lane, &above);
+    if (lane == 0) {
+        const float t = key2f(kth);
+        tau[row] = t - fabsf(t) * 1e-5f - 1e-30f;      // the bound arithmetic of the sweep rounds: step down
     }
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // exact rescoring + top-K + certificate: one warp per row
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool better2(float ya, int ia, float yb, int ib) { return ya > yb || (ya == yb && ia < ib); }
-
-__device__ __forceinline__ void warp_insert2(float* val, int* id, int K, int Kp, float y, int j, int lane) {
-    int pos = 0;
-    for (int t = 0; t < Kp; t += 32) {
-        const int e = lane + t;
-        pos += __popc(__ballot_sync(0xffffffffu, e < K && better2(val[e], id[e], y, j)));
-    }
-    float ov[4]; int oi[4];
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int e = lane + 32 * t;
-        if (32 * t < Kp && e > pos && e < K) { ov[t] = val[e - 1]; oi[t] = id[e - 1]; }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int e = lane + 32 * t;
-        if (32 * t < Kp) {
-            if (e > pos && e < K) { val[e] = ov[t]; id[e] = oi[t]; }
-            else if (e == pos) { val[e] = y; id[e] = j; }
-        }
-    }
-    __syncwarp();
-}
-
 struct RescoreArgs {
-    const float* U; const float* I; int d; int64_t M; int64_t N;
+    const float* U; const float* I; int64_t M; int64_t N;
     const int32_t* users;
     int mode; const float* pop; const float* col_bias;
     const int64_t* mask_indptr; const int32_t* mask_items;
-    const int32_t* cand; const int32_t* cnt; int cap;
+    const int32_t* cand; const int32_t* cnt; int n_seg, seg_cap;
+    int tiles_per_split;
     const float* tau;
     int K;
+    int rc;             // per-row capacity of the compacted candidate list in shared memory
     int32_t* ids_out; float* scores_out;
     int32_t* flag;      // [M] 1 = not certified
 };
 
-__global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a, int Kp) {
-    extern __shared__ unsigned char rs_smem[];
+constexpr int SORT_MAX = 256;
+
+//  1. the row's candidate segments -> one compact id list in shared memory
+//  2. train items out: every masked item lives in exactly one segment (ascending ids) -> binary search there
+//  3. exact fp32 score (the sequential-k spec) + transform of every remaining candidate
+//  4. K-th largest exact score by radix select, survivors (>= it) bitonic-sorted by (score desc, id asc)
+//  5. certificate: no overflow and >= K unmasked candidates with exact score >= tau
+template <int D>
+__global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
+    extern __shared__ __align__(8) unsigned char rs_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    float* val = reinterpret_cast<float*>(rs_smem) + (size_t)w * Kp;
-    int* idl = reinterpret_cast<int*>(rs_smem + (size_t)4 * Kp * 4) + (size_t)w * Kp;
+    const int RC = a.rc;
+    // per warp: sortbuf[256] u64 | cid[RC] | ckey[RC] | hist[256] | soff[n_seg + 1]
+    const size_t per_warp = (size_t)SORT_MAX * 8 + (size_t)RC * 8 + 1024 + (size_t)((a.n_seg + 2) / 2 * 2) * 4;
+    unsigned char* base = rs_smem + (size_t)w * per_warp;
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(base);
+    int* cid = reinterpret_cast<int*>(base + (size_t)SORT_MAX * 8);
+    uint32_t* ckey = reinterpret_cast<uint32_t*>(base + (size_t)SORT_MAX * 8 + (size_t)RC * 4);
+    int* hist = reinterpret_cast<int*>(base + (size_t)SORT_MAX * 8 + (size_t)RC * 8);
+    int* soff = hist + 256;
     const int64_t row = (int64_t)blockIdx.x * 4 + w;
     if (row >= a.M) return;
     const int K = a.K;
-    for (int e = lane; e < Kp; e += 32) { val[e] = -INFINITY; idl[e] = 0x7fffffff; }
-    __syncwarp();
     const int u = a.users[row];
-    const float* ur = a.U + (int64_t)u * a.d;
-    int64_t lo = 0, hi = 0;
-    if (a.mask_indptr) { lo = a.mask_indptr[u]; hi = a.mask_indptr[u + 1]; }
-    const int n = a.cnt[row];
-    const float tau = a.tau[row];
-    const bool overflow = n > a.cap;
-    const int nn = overflow ? a.cap : n;
-    int n_cert = 0;
-    for (int base = 0; base < nn; base += 32) {
-        const int c = base + lane;
-        float y = -INFINITY;
-        int j = 0x7fffffff;
-        bool ok = false;
-        if (c < nn) {
-            j = a.cand[row * a.cap + c];
-            const float* ir = a.I + (int64_t)j * a.d;
-            float acc = 0.0f;
-            for (int k = 0; k < a.d; k += 4) {
-                const float4 uv = ldg_f4(ur + k), iv = ldg_f4(ir + k);
-                acc = fadd(acc, fmul(uv.x, iv.x)); acc = fadd(acc, fmul(uv.y, iv.y));
-                acc = fadd(acc, fmul(uv.z, iv.z)); acc = fadd(acc, fmul(uv.w, iv.w));
+    const float* ur = a.U + (int64_t)u * D;
+
+    // 1. compact
+    bool overflow = false;
+    int tot = 0;
+    for (int sg0 = 0; sg0 < a.n_seg; sg0 += 32) {
+        const int sg = sg0 + lane;
+        int n = sg < a.n_seg ? a.cnt[row * a.n_seg + sg] : 0;
+        if (n > a.seg_cap) { overflow = true; n = a.seg_cap; }
+        int incl = n;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += t;
+        }
+        if (sg < a.n_seg) soff[sg] = tot + incl - n;
+        tot += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    overflow = __any_sync(0xffffffffu, overflow) || tot > RC;
+    if (lane == 0) soff[a.n_seg] = tot;
+    __syncwarp();
+    if (overflow) { if (lane == 0) a.flag[row] = 1; return; }
+    for (int sg = 0; sg < a.n_seg; ++sg) {
+        const int o = soff[sg], nn = soff[sg + 1] - o;
+        const int32_t* cl = a.cand + (row * a.n_seg + sg) * a.seg_cap;
+        for (int c = lane; c < nn; c += 32) cid[o + c] = cl[c];
+    }
+    __syncwarp();
+
+    // 2. masked items: id -> ~id (negative)
+    if (a.mask_indptr) {
+        const int64_t lo = a.mask_indptr[u], hi = a.mask_indptr[u + 1];
+        for (int64_t z = lo + lane; z < hi; z += 32) {
+            const int32_t it = __ldg(a.mask_items + z);
+            const int sg = (it / tc::TN / a.tiles_per_split) * 2 + ((it % tc::TN) >> 7);
+            const int send = soff[sg + 1];
+            int l = soff[sg], r = send;
+            while (l < r) {
+                const int mid = (l + r) >> 1;
+                if (cid[mid] < it) l = mid + 1; else r = mid;
             }
+            if (l < send && cid[l] == it) cid[l] = ~it;
+        }
+        __syncwarp();
+    }
+
+    // 3. exact scores
+    const float tau = a.tau[row];
+    int n_cert = 0;
+    for (int c = lane; c < tot; c += 32) {
+        const int j = cid[c];
+        uint32_t key = 0;
+        if (j >= 0) {
+            const float* ir = a.I + (int64_t)j * D;
+            float4 iv[D / 4];
+#pragma unroll
+            for (int k = 0; k < D / 4; ++k) iv[k] = ldg_f4(ir + 4 * k);     // the whole row in flight at once
+            float acc = 0.0f;
+#pragma unroll
+            for (int k = 0; k < D / 4; ++k) {
+                const float4 uv = ldg_f4(ur + 4 * k);
+                acc = fadd(acc, fmul(uv.x, iv[k].x)); acc = fadd(acc, fmul(uv.y, iv[k].y));
+                acc = fadd(acc, fmul(uv.z, iv[k].z)); acc = fadd(acc, fmul(uv.w, iv[k].w));
+            }
+            float y;
             if (a.mode == 1) y = fmul(elu_p1(acc), __ldg(a.pop + j));
             else y = a.col_bias ? fadd(acc, __ldg(a.col_bias + j)) : acc;
-            ok = !(hi > lo && csr_row_contains(a.mask_items, lo, hi, j));
-            if (!ok) y = -INFINITY;
+            key = f2key(y);
+            if (key == 0u) key = 1u;          // (only -NaN patterns map to 0) keep 0 for "not a candidate"
+            n_cert += y >= tau;
         }
-        n_cert += __popc(__ballot_sync(0xffffffffu, ok && y >= tau));
-        float tv = val[K - 1]; int ti = idl[K - 1];
-        unsigned bal = __ballot_sync(0xffffffffu, ok && better2(y, j, tv, ti));
-        while (bal) {
-            const int src = __ffs(bal) - 1;
-            bal &= bal - 1;
-            const float yy = __shfl_sync(0xffffffffu, y, src);
-            const int jj = __shfl_sync(0xffffffffu, j, src);
-            tv = val[K - 1]; ti = idl[K - 1];
-            if (better2(yy, jj, tv, ti)) warp_insert2(val, idl, K, Kp, yy, jj, lane);
+        ckey[c] = key;
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) n_cert += __shfl_xor_sync(0xffffffffu, n_cert, off);
+    __syncwarp();
+    if (n_cert < K) { if (lane == 0) a.flag[row] = 1; return; }
+
+    // 4. select + sort
+    int above;
+    const uint32_t kth = warp_kth_largest(ckey, tot, K, hist, lane, &above);
+    int ns = 0;
+    for (int c0 = 0; c0 < tot; c0 += 32) {
+        const int c = c0 + lane;
+        const bool keep = c < tot && ckey[c] >= kth;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int pos = ns + __popc(bal & ((1u << lane) - 1u));
+            if (pos < SORT_MAX) sortbuf[pos] = ((unsigned long long)ckey[c] << 32) | (uint32_t)(0x7fffffff - cid[c]);
+        }
+        ns += __popc(bal);
+    }
+    if (ns > SORT_MAX) { if (lane == 0) a.flag[row] = 1; return; }     // a huge tie at the K-th score: exact kernel
+    int n2 = 64;
+    while (n2 < ns) n2 <<= 1;
+    for (int c = ns + lane; c < n2; c += 32) sortbuf[c] = 0ull;
+    __syncwarp();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+            for (int idx = lane; idx < n2; idx += 32) {
+                const int ixj = idx ^ jj;
+                if (ixj > idx) {
+                    const unsigned long long x = sortbuf[idx], y = sortbuf[ixj];
+                    const bool desc = (idx & k) == 0;        // descending overall
+                    if (desc ? x < y : x > y) { sortbuf[idx] = y; sortbuf[ixj] = x; }
+                }
+            }
+            __syncwarp();
         }
     }
-    const bool certified = !overflow && n_cert >= K;
-    if (lane == 0) a.flag[row] = certified ? 0 : 1;
+    if (lane == 0) a.flag[row] = 0;
     for (int e = lane; e < K; e += 32) {
-        const int idv = idl[e];
-        a.ids_out[row * K + e] = idv == 0x7fffffff ? -1 : idv;
-        if (a.scores_out) a.scores_out[row * K + e] = val[e];
+        const unsigned long long kv = sortbuf[e];
+        a.ids_out[row * K + e] = 0x7fffffff - (int32_t)(uint32_t)(kv & 0xffffffffu);
+        if (a.scores_out) a.scores_out[row * K + e] = key2f((uint32_t)(kv >> 32));
     }
 }
 
@@ -552,12 +725,12 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->N_pad = (a.N + TN - 1) / TN * TN;
     p->n_tiles = (int)(p->N_pad / TN);
     const int64_t n_chunks = (int64_t)p->n_tiles * 8;
-    int se = 4;
+    // pass A samples every se-th tile; its cost ~ 1/se, the candidate count ~ se: keep as many chunk maxima per row
+    // as the selection kernel holds in shared memory
+    int se = 1;
     while ((n_chunks + se - 1) / se > TAU_MAX_KEYS) ++se;
-    if ((p->n_tiles + se - 1) / se * 8 < 4 * a.K) se = 1;
     p->se = se;
     p->n_c = (p->n_tiles + se - 1) / se * 8;
-    p->cap = a.N <= 262144 ? 1024 : 2048;
     const int m_tiles = (int)(p->M_pad / TM);
     int splits = (148 * 2 + m_tiles - 1) / m_tiles;
     if (splits < 1) splits = 1;
@@ -565,6 +738,12 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->tiles_per_split = (p->n_tiles + splits - 1) / splits;
     p->tiles_per_split = (p->tiles_per_split + se - 1) / se * se;    // splits start on sampled tiles
     p->splits = (p->n_tiles + p->tiles_per_split - 1) / p->tiles_per_split;
+    // candidate lists: one segment per (item split, column half); twice the expected total as head-room
+    p->n_seg = p->splits * 2;
+    const int cap_total = a.N <= 262144 ? 1024 : 4096;
+    p->seg_cap = ((2 * cap_total + p->n_seg - 1) / p->n_seg + 31) / 32 * 32;
+    if (p->seg_cap < 64) p->seg_cap = 64;
+    p->rc = cap_total <= 1024 ? 1024 : 2048;
     size_t o = 0;
     p->o_Ib = o; o += al256((size_t)p->N_pad * a.d * 2);
     p->o_Ub = o; o += al256((size_t)p->M_pad * a.d * 2);
@@ -573,8 +752,8 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->o_tnorm = o; o += al256((size_t)p->n_tiles * 4);
     p->o_cmax = o; o += al256((size_t)p->n_c * p->M_pad * 4);
     p->o_tau = o; o += al256((size_t)p->M_pad * 4);
-    p->o_cnt = o; o += al256((size_t)p->M_pad * 4);
-    p->o_cand = o; o += al256((size_t)p->M_pad * p->cap * 4);
+    p->o_cnt = o; o += al256((size_t)p->M_pad * p->n_seg * 4);
+    p->o_cand = o; o += al256((size_t)p->M_pad * p->n_seg * p->seg_cap * 4);
     p->o_flag = o; o += al256((size_t)p->M_pad * 4);
     p->o_frows = o; o += al256((size_t)p->M_pad * 4);
     p->o_fusers = o; o += al256((size_t)p->M_pad * 4);
@@ -618,7 +797,6 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, cudaS
     tc_convert_rows_kernel<<<(unsigned)((p.N_pad * 32 + 255) / 256), 256, 0, st>>>(a.I, nullptr, a.N, p.N_pad, a.d, Ib, inorm);
     tc_convert_rows_kernel<<<(unsigned)((p.M_pad * 32 + 255) / 256), 256, 0, st>>>(a.U, a.users, a.M, p.M_pad, a.d, Ub, unorm);
     tc_tile_norm_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(inorm, p.n_tiles, tnorm);
-    cudaMemsetAsync(cnt, 0, (size_t)p.M_pad * 4, st);
     cudaMemsetAsync(nflag, 0, 4, st);
 
     CUtensorMap tmA, tmB;
@@ -631,23 +809,30 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, cudaS
     s.c_err = 1.02f / 256.0f + (float)a.d / 2097152.0f;
     s.unorm = unorm; s.tile_inorm = tnorm;
     s.col = a.mode == 1 ? a.pop : a.col_bias;
-    s.cmax = cmax; s.tau = tau; s.cand = cand; s.cnt = cnt; s.cap = p.cap;
+    s.cmax = cmax; s.tau = tau; s.cand = cand; s.cnt = cnt; s.n_seg = p.n_seg; s.seg_cap = p.seg_cap;
 
     int rc = a.mode == 1 ? launch_sweep<1, 0>(tmA, tmB, s, p, m_tiles, st) : launch_sweep<0, 0>(tmA, tmB, s, p, m_tiles, st);
     if (rc) return 10 + rc;
-    tc_tau_select_kernel<<<(unsigned)((p.M_pad + 3) / 4), 128, 0, st>>>(cmax, p.n_c, a.M, p.M_pad, p.se, a.users, a.mask_indptr,
-                                                                         a.mask_items, a.K, tau, cnt, p.cap);
+    tc_tau_select_kernel<<<(unsigned)((p.M_pad + 3) / 4), 128, (size_t)4 * (p.n_c + 256) * 4, st>>>(cmax, p.n_c, a.M, p.M_pad, p.se, a.users, a.mask_indptr,
+                                                                         a.mask_items, a.K, tau);
     rc = a.mode == 1 ? launch_sweep<1, 1>(tmA, tmB, s, p, m_tiles, st) : launch_sweep<0, 1>(tmA, tmB, s, p, m_tiles, st);
     if (rc) return 20 + rc;
 
     RescoreArgs r;
     memset(&r, 0, sizeof(r));
-    r.U = a.U; r.I = a.I; r.d = a.d; r.M = a.M; r.N = a.N; r.users = a.users; r.mode = a.mode; r.pop = a.pop;
+    r.U = a.U; r.I = a.I; r.M = a.M; r.N = a.N; r.users = a.users; r.mode = a.mode; r.pop = a.pop;
     r.col_bias = a.col_bias; r.mask_indptr = a.mask_indptr; r.mask_items = a.mask_items;
-    r.cand = cand; r.cnt = cnt; r.cap = p.cap; r.tau = tau; r.K = a.K; r.ids_out = a.ids_out; r.scores_out = a.scores_out;
-    r.flag = flag;
-    const int Kp = (a.K + 31) / 32 * 32;
-    tc_rescore_kernel<<<(unsigned)((a.M + 3) / 4), 128, (size_t)4 * Kp * 8, st>>>(r, Kp);
+    r.cand = cand; r.cnt = cnt; r.n_seg = p.n_seg; r.seg_cap = p.seg_cap; r.tiles_per_split = p.tiles_per_split;
+    r.tau = tau; r.K = a.K; r.rc = p.rc;
+    r.ids_out = a.ids_out; r.scores_out = a.scores_out; r.flag = flag;
+    const size_t rs_smem = (size_t)4 * ((size_t)SORT_MAX * 8 + (size_t)p.rc * 8 + 1024 + (size_t)((p.n_seg + 2) / 2 * 2) * 4);
+    if (a.d == 64) {
+        cudaFuncSetAttribute(tc_rescore_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem);
+        tc_rescore_kernel<64><<<(unsigned)((a.M + 3) / 4), 128, rs_smem, st>>>(r);
+    } else {
+        cudaFuncSetAttribute(tc_rescore_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem);
+        tc_rescore_kernel<128><<<(unsigned)((a.M + 3) / 4), 128, rs_smem, st>>>(r);
+    }
     tc_compact_flags_kernel<<<148, 256, 0, st>>>(flag, a.M, a.users, frows, fusers, nflag);
 
     // rows without a certificate: the exact kernel, sized on the device (CTAs beyond ceil(n/64) exit at once)

@@ -56,7 +56,7 @@ struct EvalArgs {
 // plan + scratch layout of the tensor-core filter (pda_eval_tc.cu)
 struct TcPlan {
     int64_t M_pad, N_pad;
-    int n_tiles, se, n_c, cap, splits, tiles_per_split;
+    int n_tiles, se, n_c, splits, tiles_per_split, n_seg, seg_cap, rc;
     size_t o_Ib, o_Ub, o_inorm, o_unorm, o_tnorm, o_cmax, o_tau, o_cnt, o_cand, o_flag, o_frows, o_fusers, o_nflag;
 };
 
