@@ -171,7 +171,7 @@ struct SweepArgs {
     const float* tile_inorm;   // [n_tiles]
     const float* col;          // mode 1: pop [N]; mode 0: col_bias [N] or nullptr
     // pass A
-    float* cmax;               // [n_c][M_pad]
+    float* cmax; int n_c;      // [M_pad][n_c] chunk maxima, row-major
     // pass B
     const float* tau;          // [M_pad]
     int32_t* cand;             // [M_pad][n_seg][seg_cap] item ids, ascending inside a segment;
@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             mbar_wait(bar_tfull + 8 * acc, aph);
             fence_after();
             uint32_t va[32], vb[32];
+            float bests[4];
             const uint32_t tbase = lane_base + (uint32_t)(acc * TN);
             tmem_ld32(tbase, va);
 #pragma unroll
@@ -344,8 +345,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                             best = fmaxf(best, y);
                         }
                     }
-                    const int sc_idx = (t / a.se) * 8 + h * 4 + cc;
-                    a.cmax[(int64_t)sc_idx * a.M_pad + row] = best;
+                    bests[cc] = best;
                 } else {
                     uint32_t hits = 0;
                     if (MODE == 1) {
@@ -387,6 +387,9 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                     }
                 }
             }
+            if (PASS == 0)   // this thread's four chunk maxima of the tile: one 16 B store, row-major [row][n_c]
+                *reinterpret_cast<float4*>(a.cmax + (int64_t)row * a.n_c + (t / a.se) * 8 + h * 4) =
+                    make_float4(bests[0], bests[1], bests[2], bests[3]);
         }
         if (PASS == 1) a.cnt[(int64_t)row * a.n_seg + seg] = n_local;
     }
@@ -475,7 +478,7 @@ __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restr
     uint32_t* kk = tau_keys + (size_t)w * (n_c + 256);
     int* hist = reinterpret_cast<int*>(kk + n_c);
     for (int c = lane; c < n_c; c += 32) {
-        const float v = cmax[(int64_t)c * M_pad + row];
+        const float v = cmax[row * n_c + c];
         kk[c] = v > -INFINITY ? f2key(v) : 0u;    // 0 sorts below every real value
     }
     __syncwarp();
@@ -743,7 +746,8 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     const int cap_total = a.N <= 262144 ? 1024 : 4096;
     p->seg_cap = ((2 * cap_total + p->n_seg - 1) / p->n_seg + 31) / 32 * 32;
     if (p->seg_cap < 64) p->seg_cap = 64;
-    p->rc = cap_total <= 1024 ? 1024 : 2048;
+    // compacted list a rescoring warp holds in shared memory: ~K * (1 + se) * 1.6 entries expected
+    p->rc = p->se <= 2 ? 512 : (p->se <= 6 ? 1024 : 2048);
     size_t o = 0;
     p->o_Ib = o; o += al256((size_t)p->N_pad * a.d * 2);
     p->o_Ub = o; o += al256((size_t)p->M_pad * a.d * 2);
@@ -809,7 +813,7 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, cudaS
     s.c_err = 1.02f / 256.0f + (float)a.d / 2097152.0f;
     s.unorm = unorm; s.tile_inorm = tnorm;
     s.col = a.mode == 1 ? a.pop : a.col_bias;
-    s.cmax = cmax; s.tau = tau; s.cand = cand; s.cnt = cnt; s.n_seg = p.n_seg; s.seg_cap = p.seg_cap;
+    s.cmax = cmax; s.n_c = p.n_c; s.tau = tau; s.cand = cand; s.cnt = cnt; s.n_seg = p.n_seg; s.seg_cap = p.seg_cap;
 
     int rc = a.mode == 1 ? launch_sweep<1, 0>(tmA, tmB, s, p, m_tiles, st) : launch_sweep<0, 0>(tmA, tmB, s, p, m_tiles, st);
     if (rc) return 10 + rc;
