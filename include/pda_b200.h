@@ -97,6 +97,17 @@ int pda_get_adam_powers(pda_model* m, float* b1p_b2p_host);   /* beta1_power, be
 int pda_set_adam_powers(pda_model* m, const float* b1p_b2p_host);
 int pda_synchronize(pda_model* m);
 
+/* How the TF1 Adam sweep is evaluated.  TF1's Adam on IndexedSlices updates EVERY row at EVERY step (model_api.py:83 ->
+ * AdamOptimizer._apply_sparse_shared).  PDA_ADAM_DENSE does exactly that sweep.  PDA_ADAM_LAZY (default for BPRMF /
+ * PD / PDG) produces bit-identical tables without the sweep: a row replays the zero-gradient steps it skipped, in
+ * registers, with the same fp32 operations and the same per-step lr_t, when it is next sampled or when the tables
+ * are read (eval, pda_get_table, ...).  PDA_ADAM_LAZY_USERS: lazy user table, dense item table (data-parallel runs whose
+ * item gradient is all-reduced).  BPR(t)-pop always runs dense. */
+#define PDA_ADAM_DENSE 0
+#define PDA_ADAM_LAZY 1
+#define PDA_ADAM_LAZY_USERS 2
+int pda_set_adam_mode(pda_model* m, int mode);
+
 /* per-kernel device timing with CUDA events recorded on the launching stream around each kernel:
  * kinds PDA_PROF_*; pda_profile_read synchronises, returns the summed milliseconds and launch count
  * per kind since the last read (arrays of PDA_PROF_KINDS) and resets the counters. */

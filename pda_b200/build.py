@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libpda_b200.so")
-SOURCES = ["pda_capi.cu", "pda_train.cu", "pda_eval_exact.cu", "pda_eval_tc.cu"]
+SOURCES = ["pda_capi.cu", "pda_train.cu", "pda_adam_lazy.cu", "pda_eval_exact.cu", "pda_eval_tc.cu"]
 HEADERS = ["pda_common.cuh", "pda_kernels.h", os.path.join("..", "..", "include", "pda_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math=false",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "-shared", "-cudart", "static"]

@@ -1,0 +1,197 @@
+// Exact lazy evaluation of TF1's dense Adam sweep (reference: MF/model_api.py:83,471 ->
+// tf.train.AdamOptimizer._apply_sparse_shared of TF 1.14).
+//
+// TF1's Adam on IndexedSlices is NOT lazy: at every step it decays m and v and moves the variable for EVERY row of
+// the table, sampled or not.  For a row whose gradient is zero at step s that update is
+//     m <- m*b1 ;  v <- v*b2 ;  w <- w - (lr_s * m) / (sqrt(v) + eps)
+// -- a function of the row's own (w, m, v) and the scalar lr_s only.  So instead of sweeping the whole table every
+// step (34 GB of traffic per step on the 10M x 1M x 128 synthetic set), a row is brought up to date when it is next
+// needed, by REPLAYING the skipped steps in registers with exactly the fp32 operations the dense sweep would have
+// executed, in the same order, with the same per-step lr_s (kept in lr_hist[]).  The result is bit-identical to the
+// dense sweep (tests/test_gpu_train.py::test_lazy_adam_*); only the memory traffic differs.
+//
+//   applied[row]  number of Adam steps already applied to the row (0 .. step_no)
+//   stamp[row]    claim word: 2*(step+1)+phase of the last kernel phase that owned the row (0 = never touched:
+//                 m = v = 0, every skipped step is the identity, nothing to replay)
+//
+// Per step t:  catch-up  rows of the batch: replay steps applied[row] .. t-1           (before the forward pass)
+//              fused BPR step kernel (unchanged)                                        -> G
+//              apply     rows of the batch: step t with the summed gradient G, G <- 0, applied[row] = t+1
+// Duplicate rows inside a batch are claimed once with atomicExch on stamp[row].
+// Flush (before eval / table read-out / dense phases): every row replays up to step_no.
+#include "pda_kernels.h"
+
+namespace pda {
+
+__device__ __forceinline__ void adam_zero_grad_step(float& w, float& m, float& v, float lr_s) {
+    // adam_dense_kernel's update with g == 0: m*b1 + 0*omb1 == m*b1 and v*b2 + (0*0)*omb2 == v*b2 exactly
+    m = fmul(m, 0.9f);
+    v = fmul(v, 0.999f);
+    w = fsub(w, fdiv(fmul(lr_s, m), fadd(fsqrt(v), 1e-8f)));
+}
+
+__device__ __forceinline__ void adam_grad_step(float& w, float& m, float& v, float g, float lr_t) {
+    const float omb1 = fsub(1.0f, 0.9f), omb2 = fsub(1.0f, 0.999f);
+    m = fadd(fmul(m, 0.9f), fmul(g, omb1));
+    v = fadd(fmul(v, 0.999f), fmul(fmul(g, g), omb2));
+    w = fsub(w, fdiv(fmul(lr_t, m), fadd(fsqrt(v), 1e-8f)));
+}
+
+__device__ __forceinline__ void replay4(float4& w, float4& m, float4& v, const float* __restrict__ lr_hist, int64_t from,
+                                        int64_t to) {
+    if (m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f)
+        return;   // 0*b = 0 and 0/(0+eps) = 0: the identity
+    for (int64_t s = from; s < to; ++s) {
+        const float lr_s = __ldg(lr_hist + s);
+        adam_zero_grad_step(w.x, m.x, v.x, lr_s);
+        adam_zero_grad_step(w.y, m.y, v.y, lr_s);
+        adam_zero_grad_step(w.z, m.z, v.z, lr_s);
+        adam_zero_grad_step(w.w, m.w, v.w, lr_s);
+    }
+}
+
+// PHASE 0: catch-up to step t.  PHASE 1: apply step t with gradient.  One group of G lanes per batch entry
+// (entry e < B: user row, B <= e < 2B: pos item row, else neg item row), C float4 chunks per lane.
+template <int G, int C, int PHASE>
+__global__ void __launch_bounds__(256) adam_lazy_rows_kernel(LazyArgs a) {
+    constexpr int GPW = 32 / G;
+    const int lane = threadIdx.x & 31, gl = lane % G, gw = lane / G;
+    const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int q = a.d >> 2;
+    const int64_t t = a.step_no;
+    const int32_t claim = (int32_t)(2 * (t + 1) + PHASE);
+    float lr_t = 0.f;
+    if (PHASE == 1) {
+        const float b1p = a.pw[0], b2p = a.pw[1];
+        lr_t = fdiv(fmul(a.lr, fsqrt(fsub(1.0f, b2p))), fsub(1.0f, b1p));
+    }
+    const int64_t n_entries = 3 * a.B;
+    for (int64_t base = warp_global * GPW; base < n_entries; base += n_warps * GPW) {
+        const int64_t e = base + gw;
+        const bool valid = e < n_entries;
+        int tbl = 0;
+        int64_t row = 0;
+        if (valid) {
+            tbl = e < a.B ? 0 : 1;
+            row = e < a.B ? __ldg(a.users + e) : (e < 2 * a.B ? __ldg(a.pos + (e - a.B)) : __ldg(a.neg + (e - 2 * a.B)));
+        }
+        const bool lazy_tbl = valid && a.lazy[tbl];
+        int32_t old = claim;
+        if (lazy_tbl && gl == 0) old = atomicExch(a.stamp[tbl] + row, claim);     // first claimant of the row owns it
+        old = __shfl_sync(0xffffffffu, old, gw * G);
+        const bool mine = lazy_tbl && old != claim;
+        if (!mine) continue;
+        int32_t* ap = a.applied[tbl] + row;
+        const int64_t done = *ap;
+        float* Wr = a.W[tbl] + row * a.d;
+        float* Mr = a.m[tbl] + row * a.d;
+        float* Vr = a.v[tbl] + row * a.d;
+        if (PHASE == 0) {
+            if (done < t && old != 0) {   // old == 0: never touched, m = v = 0, nothing to replay
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const int ch = gl + G * c;
+                    if (ch < q) {
+                        float4 w = *reinterpret_cast<float4*>(Wr + 4 * ch), m = *reinterpret_cast<float4*>(Mr + 4 * ch),
+                               v = *reinterpret_cast<float4*>(Vr + 4 * ch);
+                        replay4(w, m, v, a.lr_hist, done, t);
+                        *reinterpret_cast<float4*>(Wr + 4 * ch) = w;
+                        *reinterpret_cast<float4*>(Mr + 4 * ch) = m;
+                        *reinterpret_cast<float4*>(Vr + 4 * ch) = v;
+                    }
+                }
+            }
+            if (gl == 0) *ap = (int32_t)t;
+        } else {
+            float* Gr = a.G[tbl] + row * a.d;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const int ch = gl + G * c;
+                if (ch < q) {
+                    float4 w = *reinterpret_cast<float4*>(Wr + 4 * ch), m = *reinterpret_cast<float4*>(Mr + 4 * ch),
+                           v = *reinterpret_cast<float4*>(Vr + 4 * ch), g = *reinterpret_cast<float4*>(Gr + 4 * ch);
+                    adam_grad_step(w.x, m.x, v.x, g.x, lr_t);
+                    adam_grad_step(w.y, m.y, v.y, g.y, lr_t);
+                    adam_grad_step(w.z, m.z, v.z, g.z, lr_t);
+                    adam_grad_step(w.w, m.w, v.w, g.w, lr_t);
+                    *reinterpret_cast<float4*>(Wr + 4 * ch) = w;
+                    *reinterpret_cast<float4*>(Mr + 4 * ch) = m;
+                    *reinterpret_cast<float4*>(Vr + 4 * ch) = v;
+                    *reinterpret_cast<float4*>(Gr + 4 * ch) = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            }
+            if (gl == 0) *ap = (int32_t)(t + 1);
+        }
+    }
+}
+
+template <int G, int C>
+static void launch_rows_gc(const LazyArgs& a, int phase, int grid, cudaStream_t st) {
+    if (phase == 0) adam_lazy_rows_kernel<G, C, 0><<<grid, 256, 0, st>>>(a);
+    else adam_lazy_rows_kernel<G, C, 1><<<grid, 256, 0, st>>>(a);
+}
+
+int launch_adam_lazy_rows(const LazyArgs& a, int phase, cudaStream_t st) {
+    if (a.d % 4 != 0 || a.d < 4 || a.d > 512) return 1;
+    const int q = a.d / 4;
+    int G = 1;
+    while (G < q && G < 32) G *= 2;
+    const int C = (q + G - 1) / G;
+    const int64_t warps_needed = (3 * a.B + (32 / G) - 1) / (32 / G);
+    int64_t blocks = (warps_needed + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    const int grid = (int)blocks;
+    switch (G) {
+        case 1: launch_rows_gc<1, 1>(a, phase, grid, st); break;
+        case 2: launch_rows_gc<2, 1>(a, phase, grid, st); break;
+        case 4: launch_rows_gc<4, 1>(a, phase, grid, st); break;
+        case 8: launch_rows_gc<8, 1>(a, phase, grid, st); break;
+        case 16: launch_rows_gc<16, 1>(a, phase, grid, st); break;
+        default:
+            if (C == 1) launch_rows_gc<32, 1>(a, phase, grid, st);
+            else if (C == 2) launch_rows_gc<32, 2>(a, phase, grid, st);
+            else if (C == 3) launch_rows_gc<32, 3>(a, phase, grid, st);
+            else launch_rows_gc<32, 4>(a, phase, grid, st);
+    }
+    return 0;
+}
+
+// flush: every row of table `tbl` replays up to step_no.  One warp per row (grid-stride), lane-strided float4 chunks.
+__global__ void __launch_bounds__(256) adam_lazy_flush_kernel(LazyArgs a, int tbl, int64_t n_rows) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int q = a.d >> 2;
+    const int64_t t = a.step_no;
+    for (int64_t row = warp_global; row < n_rows; row += n_warps) {
+        int32_t* ap = a.applied[tbl] + row;
+        const int64_t done = *ap;
+        if (done >= t) continue;
+        if (a.stamp[tbl][row] != 0) {
+            float* Wr = a.W[tbl] + row * a.d;
+            float* Mr = a.m[tbl] + row * a.d;
+            float* Vr = a.v[tbl] + row * a.d;
+            for (int ch = lane; ch < q; ch += 32) {
+                float4 w = *reinterpret_cast<float4*>(Wr + 4 * ch), m = *reinterpret_cast<float4*>(Mr + 4 * ch),
+                       v = *reinterpret_cast<float4*>(Vr + 4 * ch);
+                replay4(w, m, v, a.lr_hist, done, t);
+                *reinterpret_cast<float4*>(Wr + 4 * ch) = w;
+                *reinterpret_cast<float4*>(Mr + 4 * ch) = m;
+                *reinterpret_cast<float4*>(Vr + 4 * ch) = v;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) *ap = (int32_t)t;
+    }
+}
+
+void launch_adam_lazy_flush(const LazyArgs& a, int tbl, int64_t n_rows, cudaStream_t st) {
+    int64_t blocks = (n_rows + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    adam_lazy_flush_kernel<<<(int)blocks, 256, 0, st>>>(a, tbl, n_rows);
+}
+
+}  // namespace pda

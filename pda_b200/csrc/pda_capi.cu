@@ -11,6 +11,7 @@
 #include "pda_kernels.h"
 
 #define PDA_PROF_SLOTS 1024
+#define PDA_LR_CAP (1 << 22)   /* lr_t history ring of the lazy Adam replay (steps between two forced flushes) */
 
 using namespace pda;
 
@@ -38,6 +39,10 @@ struct pda_model {
     float *W[4], *Mo[4], *Vo[4], *G[4];   // 0 = user table, 1 = item table, 2 = user_temp_bias, 3 = item_temp_init_bias
     int64_t rows[4]; int cols[4]; int64_t n4[4];   // logical shape and padded float4 count of each array
     int n_arr;                                      // 2, or 4 for BPR(t)-pop
+    // exact lazy replay of the dense Adam sweep (pda_adam_lazy.cu)
+    int adam_lazy[2]; int32_t* applied[2]; int32_t* stamp[2];
+    float* lr_hist; int64_t step_no, lr_base;
+    const int32_t *cur_users, *cur_pos, *cur_neg; int64_t cur_B;   // batch of the step in flight
     float* pw;          // {beta1_power, beta2_power}
     double* loss_acc;   // {sum log(sigmoid+1e-10), sum of squares}
     float* loss3;       // device {loss, mf, reg}
@@ -154,6 +159,12 @@ int pda_create(const pda_config* cfg, pda_model** out) {
         CK(cudaMemset(m->W[t], 0, n * 4)); CK(cudaMemset(m->Mo[t], 0, n * 4));
         CK(cudaMemset(m->Vo[t], 0, n * 4)); CK(cudaMemset(m->G[t], 0, n * 4));
     }
+    for (int t = 0; t < 2; ++t) {
+        CK(dmalloc(&m->applied[t], (size_t)m->rows[t])); CK(dmalloc(&m->stamp[t], (size_t)m->rows[t]));
+        CK(cudaMemset(m->applied[t], 0, (size_t)m->rows[t] * 4)); CK(cudaMemset(m->stamp[t], 0, (size_t)m->rows[t] * 4));
+        m->adam_lazy[t] = cfg->train_mode == PDA_TRAIN_TEMP_POP ? 0 : 1;
+    }
+    CK(dmalloc(&m->lr_hist, (size_t)PDA_LR_CAP));
     CK(dmalloc(&m->pw, 2)); CK(dmalloc(&m->loss_acc, 2)); CK(dmalloc(&m->loss3, 4)); CK(dmalloc(&m->loss_sum, 4));
     const float pw0[2] = {0.9f, 0.999f};
     CK(cudaMemcpy(m->pw, pw0, 8, cudaMemcpyHostToDevice));
@@ -171,6 +182,8 @@ void pda_destroy(pda_model* m) {
     cudaSetDevice(m->cfg.device);
     cudaDeviceSynchronize();
     for (int t = 0; t < 4; ++t) { cudaFree(m->W[t]); cudaFree(m->Mo[t]); cudaFree(m->Vo[t]); cudaFree(m->G[t]); }
+    for (int t = 0; t < 2; ++t) { cudaFree(m->applied[t]); cudaFree(m->stamp[t]); }
+    cudaFree(m->lr_hist);
     cudaFree(m->pw); cudaFree(m->loss_acc); cudaFree(m->loss3); cudaFree(m->loss_sum); cudaFreeHost(m->loss3_pinned);
     cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
     cudaFree(m->pop_train);
@@ -237,8 +250,32 @@ int pda_init_tables(pda_model* m, uint32_t seed) {
     CK(cudaMemcpy(m->pw, pw0, 8, cudaMemcpyHostToDevice));
     CK(cudaMemset(m->loss_acc, 0, 16));
     CK(cudaMemset(m->loss_sum, 0, 32));
+    for (int t = 0; t < 2; ++t) {
+        CK(cudaMemset(m->applied[t], 0, (size_t)m->rows[t] * 4)); CK(cudaMemset(m->stamp[t], 0, (size_t)m->rows[t] * 4));
+    }
+    m->step_no = 0; m->lr_base = 0;
     CK(cudaDeviceSynchronize());
     return PDA_OK;
+}
+
+// ---- lazy Adam plumbing ----
+static void lazy_args(pda_model* m, LazyArgs* a) {
+    memset(a, 0, sizeof(*a));
+    for (int t = 0; t < 2; ++t) {
+        a->W[t] = m->W[t]; a->m[t] = m->Mo[t]; a->v[t] = m->Vo[t]; a->G[t] = m->G[t];
+        a->applied[t] = m->applied[t]; a->stamp[t] = m->stamp[t]; a->lazy[t] = m->adam_lazy[t];
+    }
+    a->users = m->cur_users; a->pos = m->cur_pos; a->neg = m->cur_neg; a->B = m->cur_B; a->d = m->d;
+    a->step_no = m->step_no; a->lr_hist = m->lr_hist - m->lr_base; a->pw = m->pw; a->lr = m->cfg.lr;
+}
+
+// every lazily maintained row replays up to step_no: after this the tables hold what the dense sweep would hold
+static void flush_lazy(pda_model* m, cudaStream_t st) {
+    if (!m->adam_lazy[0] && !m->adam_lazy[1]) return;
+    LazyArgs a;
+    lazy_args(m, &a);
+    for (int t = 0; t < 2; ++t)
+        if (m->adam_lazy[t]) { ProfScope ps(m, PDA_PROF_ADAM, st); launch_adam_lazy_flush(a, t, m->rows[t], st); }
 }
 
 // *n = number of fp32 elements of the selected array (rows x cols)
@@ -269,7 +306,10 @@ int pda_set_table(pda_model* m, int which, const float* src) {
     int64_t rows; float* p = table_of(m, which, &rows);
     if (!p) return fail(PDA_ERR_ARG, "unknown table %d", which);
     CK(cudaSetDevice(m->cfg.device));
+    flush_lazy(m, 0);
     CK(cudaMemcpy(p, src, (size_t)rows * 4, cudaMemcpyHostToDevice));
+    // a row whose slots were just overwritten may hold non-zero m / v: it is no longer "never touched"
+    for (int t = 0; t < 2; ++t) launch_fill_i32(m->stamp[t], m->rows[t], 1, 0);
     return PDA_OK;
 }
 int pda_get_table(pda_model* m, int which, float* dst) {
@@ -277,6 +317,7 @@ int pda_get_table(pda_model* m, int which, float* dst) {
     int64_t rows; float* p = table_of(m, which, &rows);
     if (!p) return fail(PDA_ERR_ARG, "unknown table %d", which);
     CK(cudaSetDevice(m->cfg.device));
+    flush_lazy(m, 0);
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(dst, p, (size_t)rows * 4, cudaMemcpyDeviceToHost));
     return PDA_OK;
@@ -284,7 +325,30 @@ int pda_get_table(pda_model* m, int which, float* dst) {
 void* pda_table_ptr(pda_model* m, int which) {
     if (!m) return nullptr;
     int64_t rows;
+    cudaSetDevice(m->cfg.device);
+    flush_lazy(m, 0);          // the caller reads the table itself: make it current first
+    cudaDeviceSynchronize();
     return table_of(m, which, &rows);
+}
+
+int pda_set_adam_mode(pda_model* m, int mode) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    if (mode != PDA_ADAM_DENSE && mode != PDA_ADAM_LAZY && mode != PDA_ADAM_LAZY_USERS)
+        return fail(PDA_ERR_ARG, "unknown adam mode %d", mode);
+    if (mode != PDA_ADAM_DENSE && m->cfg.train_mode == PDA_TRAIN_TEMP_POP)
+        return fail(PDA_ERR_ARG, "the lazy Adam replay covers the two embedding tables only; BPR(t)-pop runs the dense sweep");
+    CK(cudaSetDevice(m->cfg.device));
+    flush_lazy(m, 0);
+    const int want[2] = {mode != PDA_ADAM_DENSE, mode == PDA_ADAM_LAZY};
+    for (int t = 0; t < 2; ++t) {
+        if (want[t] && !m->adam_lazy[t]) {   // dense -> lazy: every row is current and may carry non-zero slots
+            launch_fill_i32(m->applied[t], m->rows[t], (int32_t)m->step_no, 0);
+            launch_fill_i32(m->stamp[t], m->rows[t], 1, 0);
+        }
+        m->adam_lazy[t] = want[t];
+    }
+    CK(cudaDeviceSynchronize());
+    return PDA_OK;
 }
 int pda_get_adam_powers(pda_model* m, float* out) {
     if (!m || !out) return fail(PDA_ERR_ARG, "null argument");
@@ -435,6 +499,13 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
     m->last_B = m->global_batch > 0 ? m->global_batch : B;
     s.invB = 1.0f / (float)m->last_B;
     s.loss_acc = m->loss_acc;
+    m->cur_users = users; m->cur_pos = pos; m->cur_neg = neg; m->cur_B = B;
+    if (m->adam_lazy[0] || m->adam_lazy[1]) {   // rows of this batch replay the steps they skipped, before they are read
+        LazyArgs la;
+        lazy_args(m, &la);
+        ProfScope ps(m, PDA_PROF_ADAM, st);
+        if (launch_adam_lazy_rows(la, 0, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
+    }
     s.pop_mode = m->cfg.train_mode == PDA_TRAIN_S_CONDITION ? 1 : m->cfg.train_mode == PDA_TRAIN_TEMP_POP ? 2 : 0;
     s.uniq_users = uniq;
     if (s.pop_mode == 2) {   // BPR(t)-pop: the stage of each triple rides in the internal batch (b_time)
@@ -452,17 +523,37 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
 
 // TF1 Adam sweep over both tables (one kernel) + loss / beta-power bookkeeping
 static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st) {
+    float* lr_slot = nullptr;
     if (apply_adam) {
+        const bool any_lazy = m->adam_lazy[0] || m->adam_lazy[1];
+        if (any_lazy) {
+            if (!m->cur_users) return fail(PDA_ERR_STATE, "pda_adam_apply without a preceding forward/backward");
+            LazyArgs la;
+            lazy_args(m, &la);
+            ProfScope ps(m, PDA_PROF_ADAM, st);
+            if (launch_adam_lazy_rows(la, 1, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
+        }
         AdamArgs a;
         memset(&a, 0, sizeof(a));
+        bool any_dense = false;
         for (int t = 0; t < m->n_arr; ++t) {
+            if (t < 2 && m->adam_lazy[t]) continue;     // n4 = 0: left to the lazy kernels
             a.W[t] = m->W[t]; a.m[t] = m->Mo[t]; a.v[t] = m->Vo[t]; a.G[t] = m->G[t]; a.n4[t] = m->n4[t];
+            any_dense = true;
         }
         a.pw = m->pw; a.lr = m->cfg.lr;
-        ProfScope ps(m, PDA_PROF_ADAM, st);
-        launch_adam_dense(a, st);
+        if (any_dense) { ProfScope ps(m, PDA_PROF_ADAM, st); launch_adam_dense(a, st); }
+        lr_slot = m->lr_hist + (m->step_no - m->lr_base);
     }
-    launch_finish_step(m->loss_acc, m->loss3, m->loss_sum, m->pw, m->last_B, m->cfg.regs, m->cfg.batch_size, apply_adam ? 1 : 0, st);
+    launch_finish_step(m->loss_acc, m->loss3, m->loss_sum, m->pw, m->last_B, m->cfg.regs, m->cfg.batch_size, apply_adam ? 1 : 0,
+                       m->cfg.lr, lr_slot, st);
+    if (apply_adam) {
+        ++m->step_no;
+        if (m->step_no - m->lr_base >= PDA_LR_CAP) {   // history ring full: bring every row up to date, start a new ring
+            flush_lazy(m, st);
+            m->lr_base = m->step_no;
+        }
+    }
     return PDA_OK;
 }
 
@@ -679,6 +770,7 @@ int pda_temp_item_bias_host(pda_model* m, int32_t first_user, float* out) {
 // PDA_EVAL_AUTO: the tcgen05 filter when the shape supports it (d in {64,128}, >= 4096 items) and there are enough
 // rows to fill the machine, else the exact CUDA-core kernel.  Both give identical ids and scores.
 static int do_recommend(pda_model* m, const EvalArgs& a, int backend, cudaStream_t st) {
+    flush_lazy(m, st);     // scoring reads both tables: rows that skipped Adam steps catch up first
     if (a.K < 1 || a.K > 128 || a.M < 1) return fail(PDA_ERR_ARG, "bad eval arguments (K in [1,128], M >= 1)");
     const bool tc_ok = tc_supported(a);
     if (backend == PDA_EVAL_TENSOR && !tc_ok)
@@ -801,6 +893,7 @@ int pda_scores_host(pda_model* m, const int32_t* users, int64_t M, int rec_type,
     a.U = m->W[0]; a.I = m->W[1]; a.N = m->nI; a.d = m->d; a.users = d_users; a.M = M;
     a.mode = rec_type == PDA_REC_WITH_POP ? 1 : 0; a.pop = pop ? d_pop : nullptr;
     a.K = 1; a.ids_out = nullptr; a.scores_out = nullptr; a.dense_out = d_dense;
+    flush_lazy(m, 0);
     (void)d_ids;
     if (launch_recommend_exact(a, 0)) return fail(PDA_ERR_ARG, "bad eval arguments");
     CK(cudaMemcpyAsync(out, d_dense, nd, cudaMemcpyDeviceToHost, 0));

@@ -40,6 +40,17 @@ struct AdamArgs {
     float lr;
 };
 
+// exact lazy replay of the dense Adam sweep (pda_adam_lazy.cu)
+struct LazyArgs {
+    float* W[2]; float* m[2]; float* v[2]; float* G[2];
+    int32_t* applied[2]; int32_t* stamp[2];
+    int lazy[2];                                // per table: 1 = lazy, 0 = left to the dense sweep
+    const int32_t *users, *pos, *neg; int64_t B; int d;
+    int64_t step_no;                            // steps applied so far = index of the current step
+    const float* lr_hist;                       // lr_hist[s] = lr_t of step s (pointer already offset by the ring base)
+    const float* pw; float lr;
+};
+
 struct EvalArgs {
     const float* U; const float* I; int64_t N; int d;
     const int32_t* users; int64_t M;
@@ -66,7 +77,10 @@ void launch_sampler(SamplerArgs a, cudaStream_t st);
 int launch_bpr_step(const StepArgs& a, cudaStream_t st);
 void launch_adam_dense(const AdamArgs& a, cudaStream_t st);
 void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float* pw, int64_t B, float regs,
-                        int batch_size, int advance_powers, cudaStream_t st);
+                        int batch_size, int advance_powers, float lr, float* lr_slot, cudaStream_t st);
+int launch_adam_lazy_rows(const LazyArgs& a, int phase, cudaStream_t st);
+void launch_adam_lazy_flush(const LazyArgs& a, int tbl, int64_t n_rows, cudaStream_t st);
+void launch_fill_i32(int32_t* p, int64_t n, int32_t value, cudaStream_t st);
 void launch_f32_to_i32(const float* src, int32_t* dst, int64_t n, int32_t max_value, cudaStream_t st);
 void launch_temp_item_bias(const float* ub, const float* ib, int64_t n_items, int temp_num, int32_t first_user,
                            float* out, cudaStream_t st);

@@ -338,6 +338,17 @@ void launch_adam_dense(const AdamArgs& a, cudaStream_t st) {
 }
 
 // loss3 = {loss, mf, reg}; beta powers advance (AdamOptimizer._finish); accumulators reset.
+__global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t value) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = value;
+}
+
+void launch_fill_i32(int32_t* p, int64_t n, int32_t value, cudaStream_t st) {
+    int64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    fill_i32_kernel<<<(int)blocks, 256, 0, st>>>(p, n, value);
+}
+
 // stage labels arrive as fp32 in the pos_pop slot (tf.cast(temp, tf.int32), train_new_api.py:565); clamped to
 // [0, max_value] so a bad label can never index outside item_temp_init_bias
 __global__ void f32_to_i32_kernel(const float* __restrict__ src, int32_t* __restrict__ dst, int64_t n, int32_t max_value) {
@@ -373,8 +384,10 @@ void launch_temp_item_bias(const float* ub, const float* ib, int64_t n_items, in
 // loss_sum[0..2] accumulate the fp32 step losses in double (the epoch means of train_new_api.py:1095-1097),
 // loss_sum[3] counts the steps.
 __global__ void finish_step_kernel(double* loss_acc, float* loss3, double* loss_sum, float* pw, double B, double regs,
-                                   double batch_size, int advance_powers) {
+                                   double batch_size, int advance_powers, float lr, float* lr_slot) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
+        // lr_t of the step that just ran (same expression as the Adam kernels), kept for the lazy replay
+        if (advance_powers && lr_slot) *lr_slot = fdiv(fmul(lr, fsqrt(fsub(1.0f, pw[1]))), fsub(1.0f, pw[0]));
         double mf = -loss_acc[0] / B;
         double reg = regs * 0.5 * loss_acc[1] / batch_size;
         loss3[0] = (float)(mf + reg); loss3[1] = (float)mf; loss3[2] = (float)reg;
@@ -386,9 +399,9 @@ __global__ void finish_step_kernel(double* loss_acc, float* loss3, double* loss_
 }
 
 void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float* pw, int64_t B, float regs,
-                        int batch_size, int advance_powers, cudaStream_t st) {
+                        int batch_size, int advance_powers, float lr, float* lr_slot, cudaStream_t st) {
     finish_step_kernel<<<1, 32, 0, st>>>(loss_acc, loss3, loss_sum, pw, (double)B, (double)regs, (double)batch_size,
-                                         advance_powers);
+                                         advance_powers, lr, lr_slot);
 }
 
 }  // namespace pda

@@ -69,6 +69,13 @@ class PDAModel:
     def init_tables(self, seed=2021):
         check(self.lib.pda_init_tables(self._h, seed))
 
+    ADAM_MODES = {"dense": 0, "lazy": 1, "lazy_users": 2}
+
+    def set_adam_mode(self, mode):
+        """'dense': TF1's every-row sweep as such; 'lazy' (default): bit-identical exact replay without the sweep;
+        'lazy_users': lazy user table + dense item table (data-parallel item-gradient all-reduce)."""
+        check(self.lib.pda_set_adam_mode(self._h, self.ADAM_MODES[mode]))
+
     def synchronize(self):
         check(self.lib.pda_synchronize(self._h))
 

@@ -35,6 +35,10 @@ class ShardedTrainer:
         self._gi = self._acc = None
         self._reduce = reducer
         if self.world > 1:
+            if hasattr(model, "set_adam_mode"):
+                # the item gradient is the sum over ranks: which item rows were touched is not known locally,
+                # so the replicated item table keeps the dense sweep; the rank-local user table stays lazy
+                model.set_adam_mode("lazy_users")
             import torch
             import torch.distributed as dist
             if reducer is None:

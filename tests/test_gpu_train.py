@@ -187,3 +187,80 @@ def test_error_paths(pda):
     with pytest.raises(pda.PdaError):
         m.set_train_csr(np.array([0] + [2] * 50), np.array([5, 3]))   # unsorted row
     m.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# exact lazy replay of the TF1 dense Adam sweep (pda_adam_lazy.cu)
+# ---------------------------------------------------------------------------------------------
+def _all_state(m):
+    return {k: m.get_table(k) for k in ("user_embedding", "item_embedding", "user_m", "user_v", "item_m", "item_v")}
+
+
+@pytest.mark.parametrize("mode,d", [("s_condition", 64), ("normal", 128), ("s_condition", 20)])
+def test_lazy_adam_bit_identical_to_dense(pda, mode, d):
+    """Same batches through the dense sweep and through the lazy replay: every table and Adam slot must agree bit for
+    bit at every read-out, including rows that were never sampled, rows sampled once and then left alone for many
+    steps, and continuing after a read-out (which flushes)."""
+    rng = np.random.default_rng(5)
+    n_users, n_items, B = 3000, 2500, 128
+    U = rng.normal(0, 0.3, (n_users, d)).astype(np.float32)
+    I = rng.normal(0, 0.3, (n_items, d)).astype(np.float32)
+    models = {}
+    for am in ("dense", "lazy"):
+        m = pda.PDAModel(n_users, n_items, d, train=mode, batch_size=B, lr=1e-2, regs=1e-3, init=False)
+        m.set_adam_mode(am)
+        m.set_table("user_embedding", U)
+        m.set_table("item_embedding", I)
+        models[am] = m
+    for step in range(40):
+        users, pos, neg, pp, npop = _random_batch(rng, n_users, n_items, B, unique_items=True)
+        if step >= 25:          # a phase that only touches a few rows: everything else accumulates a long lag
+            users = users % 200
+            users = np.unique(users)
+            k = len(users)
+            pos, neg, pp, npop = pos[:k] % 300, 300 + neg[:k] % 300, pp[:k], npop[:k]
+            _, fi = np.unique(pos, return_index=True)
+            users, pos, neg, pp, npop = users[fi], pos[fi], neg[fi], pp[fi], npop[fi]
+            _, fi = np.unique(neg, return_index=True)
+            users, pos, neg, pp, npop = users[fi], pos[fi], neg[fi], pp[fi], npop[fi]
+        la = models["lazy"].train_step(users, pos, neg, pp, npop)
+        de = models["dense"].train_step(users, pos, neg, pp, npop)
+        assert la == de, (step, la, de)
+        if step in (0, 7, 24, 39):
+            a, b = _all_state(models["lazy"]), _all_state(models["dense"])
+            for k in a:
+                assert np.array_equal(bits(a[k]), bits(b[k])), (step, k)
+    assert np.array_equal(bits(models["lazy"].get_adam_powers()), bits(models["dense"].get_adam_powers()))
+    for m in models.values():
+        m.close()
+
+
+def test_lazy_adam_mode_switches_and_eval_flush(pda, c_oracle):
+    """dense -> lazy -> dense in one run equals the oracle's dense run; recommending in lazy mode sees current tables."""
+    rng = np.random.default_rng(8)
+    n_users, n_items, B, d = 1500, 5000, 128, 64
+    U = rng.normal(0, 0.3, (n_users, d)).astype(np.float32)
+    I = rng.normal(0, 0.3, (n_items, d)).astype(np.float32)
+    m = pda.PDAModel(n_users, n_items, d, train="normal", batch_size=B, lr=1e-2, regs=1e-3, init=False)
+    m.set_table("user_embedding", U); m.set_table("item_embedding", I)
+    ref = c_oracle.CModel(U, I, 1e-2, 1e-3, B, "normal")
+    for step in range(30):
+        if step == 0:
+            m.set_adam_mode("dense")
+        if step == 10:
+            m.set_adam_mode("lazy")
+        if step == 22:
+            m.set_adam_mode("dense")
+        users, pos, neg, pp, npop = _random_batch(rng, n_users, n_items, B, unique_items=True)
+        m.train_step(users, pos, neg)
+        ref.train_step(users, pos, neg)
+        if step == 18:      # lazy phase: scoring must flush first
+            eu = np.arange(700, dtype=np.int32)
+            for backend in ("exact", "tensor"):
+                ids = m.do_recommendation(eu, None, "main_branch", K=20, mask=False, backend=backend)
+                rid, _ = c_oracle.recommend(ref.U, ref.I, eu, "main_branch", 20)
+                assert np.array_equal(ids, rid), backend
+    assert np.array_equal(bits(m.get_table("user_embedding")), bits(ref.U))
+    assert np.array_equal(bits(m.get_table("item_embedding")), bits(ref.I))
+    assert np.array_equal(bits(m.get_table("item_v")), bits(ref.vI))
+    m.close()
