@@ -34,7 +34,7 @@ SEED_DATA, SEED_SAMPLER, SEED_INIT = 2020, 2020, 2021
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--users", type=int, default=10_000_000)
@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--adam", default="lazy", choices=["lazy", "dense"],
+                    help="how the TF1 every-row Adam sweep is evaluated (bit-identical results; see DESIGN.md 5.2)")
     return ap.parse_args()
 
 
@@ -71,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
             self.proc = None
@@ -130,7 +132,9 @@ def run_ours(a):
     model.set_train_csr_device(wrap_ptr(ds["indptr"]), wrap_ptr(ds["items"]), wrap_ptr(ds["times"]), ds["nnz"],
                                wrap_ptr(ds["active"]), ds["active"].numel(), unique_times=np.arange(ds["n_stages"] - 1))
     model.set_train_pop(P.cpu().numpy())
-    trainer = ShardedTrainer(model, world, rank)
+    if a.adam == "dense":
+        model.set_adam_mode("dense")
+    trainer = ShardedTrainer(model, world, rank)      # world > 1: lazy user table + dense (all-reduced) item table
     stream = torch.cuda.current_stream().cuda_stream
 
     def barrier():
@@ -146,6 +150,8 @@ def run_ours(a):
     run_steps(0, a.warmup)
     barrier()
     model.profile(True)
+    if a.adam == "lazy":
+        model.adam_stats(reset=True)
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -160,6 +166,7 @@ def run_ours(a):
         clocks.stop()
     prof = model.profile_read()
     model.profile(False)
+    rows_updated, row_steps_replayed = model.adam_stats(reset=True) if a.adam == "lazy" else (0, 0)
     loss = model.read_loss(stream)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -222,28 +229,39 @@ def run_ours(a):
         pairs = Me * a.items
         ev = {"metric": "eval_user_item_pairs_per_sec", "value": pairs / (kms * 1e-3), "unit": "pairs/s",
               "e2e_value": pairs / wall, "users": Me, "items": a.items, "K": 50, "rec_type": "condition",
-              "backend": "exact fp32 CUDA-core scorer" if pr["eval_tensor"][1] == 0 else "tcgen05 filter + exact rescoring",
+              "backend": "exact fp32 CUDA-core scorer" if pr["eval_tensor"][1] == 0 else
+              "tcgen05 bf16 filter (kind::f16, fp32 accumulate in TMEM) + exact fp32 rescoring of the certified candidates",
+              "filter_stats": model.tc_last_stats() if pr["eval_tensor"][1] else None,
               "kernel_ms": kms,
               "roofline": {"bound": "tensor", "achieved": pairs * 2 * d / (kms * 1e-3) / 1e12, "peak": pk["bf16_sus"],
                            "unit": "TFLOP/s", "frac": pairs * 2 * d / (kms * 1e-3) / 1e12 / pk["bf16_sus"], "traffic": None,
                            "peak_source": pk["src"] + " sustained bf16"}}
 
-    # ---- roofline of the dominant kernel + the fused step kernel ----
+    # ---- per-kernel device times (CUDA events on the launching stream) and rooflines ----
     step_ms, step_n = prof["bpr_step"]
     adam_ms, adam_n = prof["adam"]
+    cat_ms, cat_n = prof["adam_catchup"]
     samp_ms, samp_n = prof["sampler"]
     bytes_triple = 24 * d + 20
     step_gbs = bytes_triple * B / (step_ms / max(step_n, 1) * 1e-3) / 1e9 if step_ms > 0 else 0.0
-    adam_bytes = (users_local + a.items) * d * 4 * 6
-    adam_gbs = adam_bytes / (adam_ms / max(adam_n, 1) * 1e-3) / 1e9 if adam_ms > 0 else 0.0
+    if a.adam == "dense" or world > 1:
+        adam_rows = (0 if (a.adam == "lazy") else users_local) + a.items      # rows swept per step
+        adam_rows += rows_updated / max(a.steps, 1)
+    else:
+        adam_rows = rows_updated / max(a.steps, 1)                           # rows updated with a gradient per step
+    adam_bytes = adam_rows * d * 4 * 6                                       # W, m, v read + written
+    adam_gbs = adam_bytes / (adam_ms / max(a.steps, 1) * 1e-3) / 1e9 if adam_ms > 0 else 0.0
     kern = {
         "bpr_step": {"ms_per_launch": step_ms / max(step_n, 1), "share_of_step": step_ms / ms, "achieved": step_gbs,
-                     "frac": step_gbs / pk["hbm"], "algorithmic_bytes": bytes_triple * B},
-        "adam_dense": {"ms_per_launch": adam_ms / max(adam_n, 1), "share_of_step": adam_ms / ms, "achieved": adam_gbs,
-                       "frac": adam_gbs / pk["hbm"], "algorithmic_bytes": adam_bytes},
+                     "frac": step_gbs / pk["hbm"], "algorithmic_bytes": bytes_triple * B, "unit": "GB/s"},
+        "adam_apply": {"ms_per_step": adam_ms / max(a.steps, 1), "launches_per_step": adam_n / max(a.steps, 1),
+                       "share_of_step": adam_ms / ms, "achieved": adam_gbs, "frac": adam_gbs / pk["hbm"],
+                       "algorithmic_bytes": adam_bytes, "rows_per_step": adam_rows, "mode": a.adam, "unit": "GB/s"},
+        "adam_catchup": {"ms_per_step": cat_ms / max(a.steps, 1), "share_of_step": cat_ms / ms,
+                         "zero_grad_row_steps_replayed_per_step": row_steps_replayed / max(a.steps, 1)},
         "sampler": {"ms_per_launch": samp_ms / max(samp_n, 1), "share_of_step": samp_ms / ms},
     }
-    dom = "adam_dense" if adam_ms > step_ms else "bpr_step"
+    dom = "adam_apply" if adam_ms > step_ms else "bpr_step"
     roof = {"bound": "hbm", "kernel": dom, "achieved": kern[dom]["achieved"], "peak": pk["hbm"], "unit": "GB/s",
             "frac": kern[dom]["frac"], "traffic": None, "peak_source": pk["src"]}
 
@@ -256,12 +274,12 @@ def run_ours(a):
                "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"synthetic {a.users} users x {a.items} items d={d}, PD (s_condition) gamma={GAMMA}, "
-                                      f"TF1-dense Adam, B={B} triples/step/GPU",
+                                      f"TF1 every-row Adam semantics ({a.adam} evaluation), B={B} triples/step/GPU",
                           "users": a.users, "items": a.items, "d": d, "batch_per_gpu": B, "global_batch": B * world,
                           "parallelism": f"user-shard x{world}, items replicated" + (" + NCCL item-grad allreduce" if world > 1 else ""),
                           "l2_policy": "tables >> L2 (user table %.1f GB per rank)" % (users_local * d * 4 / 1e9)},
                "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e, "eval": ev,
-               "gpu_launches": int(step_n + adam_n + samp_n + a.steps), "clocks": clocks.summary(),
+               "gpu_launches": int(step_n + adam_n + cat_n + samp_n + a.steps), "clocks": clocks.summary(),
                "last_loss": [float(x) for x in loss]}
         print(json.dumps(out))
     if world > 1:

@@ -107,6 +107,9 @@ int pda_synchronize(pda_model* m);
 #define PDA_ADAM_LAZY 1
 #define PDA_ADAM_LAZY_USERS 2
 int pda_set_adam_mode(pda_model* m, int mode);
+/* out[0] = rows updated with a gradient by the lazy apply kernel, out[1] = zero-gradient row-steps replayed, both since
+ * the last call with reset != 0 (synchronises the device) */
+int pda_adam_stats(pda_model* m, int64_t* out2, int reset);
 
 /* per-kernel device timing with CUDA events recorded on the launching stream around each kernel:
  * kinds PDA_PROF_*; pda_profile_read synchronises, returns the summed milliseconds and launch count
@@ -116,7 +119,8 @@ int pda_set_adam_mode(pda_model* m, int mode);
 #define PDA_PROF_ADAM 2
 #define PDA_PROF_EVAL 3
 #define PDA_PROF_EVAL_TC 4
-#define PDA_PROF_KINDS 5
+#define PDA_PROF_ADAM_CATCHUP 5   /* lazy Adam: replay of skipped steps for the rows of the batch (+ flushes) */
+#define PDA_PROF_KINDS 6
 int pda_profile_enable(pda_model* m, int on);
 int pda_profile_read(pda_model* m, double* ms_sum, int32_t* count);
 

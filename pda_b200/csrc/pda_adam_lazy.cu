@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(256) adam_lazy_rows_kernel(LazyArgs a) {
         lr_t = fdiv(fmul(a.lr, fsqrt(fsub(1.0f, b2p))), fsub(1.0f, b1p));
     }
     const int64_t n_entries = 3 * a.B;
+    unsigned long long stat = 0;   // per-lane tally, reduced once per warp at the end (one same-address atomic per warp)
     for (int64_t base = warp_global * GPW; base < n_entries; base += n_warps * GPW) {
         const int64_t e = base + gw;
         const bool valid = e < n_entries;
@@ -88,6 +89,7 @@ __global__ void __launch_bounds__(256) adam_lazy_rows_kernel(LazyArgs a) {
         float* Mr = a.m[tbl] + row * a.d;
         float* Vr = a.v[tbl] + row * a.d;
         if (PHASE == 0) {
+            if (gl == 0 && done < t && old != 0) stat += (unsigned long long)(t - done);
             if (done < t && old != 0) {   // old == 0: never touched, m = v = 0, nothing to replay
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
@@ -105,6 +107,7 @@ __global__ void __launch_bounds__(256) adam_lazy_rows_kernel(LazyArgs a) {
             if (gl == 0) *ap = (int32_t)t;
         } else {
             float* Gr = a.G[tbl] + row * a.d;
+            if (gl == 0) stat += 1ull;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const int ch = gl + G * c;
@@ -124,6 +127,9 @@ __global__ void __launch_bounds__(256) adam_lazy_rows_kernel(LazyArgs a) {
             if (gl == 0) *ap = (int32_t)(t + 1);
         }
     }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) stat += __shfl_xor_sync(0xffffffffu, stat, off);
+    if (lane == 0 && stat) atomicAdd(a.stats + (PHASE == 0 ? 1 : 0), stat);
 }
 
 template <int G, int C>

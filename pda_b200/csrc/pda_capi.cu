@@ -41,7 +41,7 @@ struct pda_model {
     int n_arr;                                      // 2, or 4 for BPR(t)-pop
     // exact lazy replay of the dense Adam sweep (pda_adam_lazy.cu)
     int adam_lazy[2]; int32_t* applied[2]; int32_t* stamp[2];
-    float* lr_hist; int64_t step_no, lr_base;
+    float* lr_hist; int64_t step_no, lr_base; unsigned long long* lazy_stats;
     const int32_t *cur_users, *cur_pos, *cur_neg; int64_t cur_B;   // batch of the step in flight
     float* pw;          // {beta1_power, beta2_power}
     double* loss_acc;   // {sum log(sigmoid+1e-10), sum of squares}
@@ -165,6 +165,7 @@ int pda_create(const pda_config* cfg, pda_model** out) {
         m->adam_lazy[t] = cfg->train_mode == PDA_TRAIN_TEMP_POP ? 0 : 1;
     }
     CK(dmalloc(&m->lr_hist, (size_t)PDA_LR_CAP));
+    CK(dmalloc(&m->lazy_stats, 2)); CK(cudaMemset(m->lazy_stats, 0, 16));
     CK(dmalloc(&m->pw, 2)); CK(dmalloc(&m->loss_acc, 2)); CK(dmalloc(&m->loss3, 4)); CK(dmalloc(&m->loss_sum, 4));
     const float pw0[2] = {0.9f, 0.999f};
     CK(cudaMemcpy(m->pw, pw0, 8, cudaMemcpyHostToDevice));
@@ -183,7 +184,7 @@ void pda_destroy(pda_model* m) {
     cudaDeviceSynchronize();
     for (int t = 0; t < 4; ++t) { cudaFree(m->W[t]); cudaFree(m->Mo[t]); cudaFree(m->Vo[t]); cudaFree(m->G[t]); }
     for (int t = 0; t < 2; ++t) { cudaFree(m->applied[t]); cudaFree(m->stamp[t]); }
-    cudaFree(m->lr_hist);
+    cudaFree(m->lr_hist); cudaFree(m->lazy_stats);
     cudaFree(m->pw); cudaFree(m->loss_acc); cudaFree(m->loss3); cudaFree(m->loss_sum); cudaFreeHost(m->loss3_pinned);
     cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
     cudaFree(m->pop_train);
@@ -267,6 +268,7 @@ static void lazy_args(pda_model* m, LazyArgs* a) {
     }
     a->users = m->cur_users; a->pos = m->cur_pos; a->neg = m->cur_neg; a->B = m->cur_B; a->d = m->d;
     a->step_no = m->step_no; a->lr_hist = m->lr_hist - m->lr_base; a->pw = m->pw; a->lr = m->cfg.lr;
+    a->stats = m->lazy_stats;
 }
 
 // every lazily maintained row replays up to step_no: after this the tables hold what the dense sweep would hold
@@ -275,7 +277,7 @@ static void flush_lazy(pda_model* m, cudaStream_t st) {
     LazyArgs a;
     lazy_args(m, &a);
     for (int t = 0; t < 2; ++t)
-        if (m->adam_lazy[t]) { ProfScope ps(m, PDA_PROF_ADAM, st); launch_adam_lazy_flush(a, t, m->rows[t], st); }
+        if (m->adam_lazy[t]) { ProfScope ps(m, PDA_PROF_ADAM_CATCHUP, st); launch_adam_lazy_flush(a, t, m->rows[t], st); }
 }
 
 // *n = number of fp32 elements of the selected array (rows x cols)
@@ -329,6 +331,15 @@ void* pda_table_ptr(pda_model* m, int which) {
     flush_lazy(m, 0);          // the caller reads the table itself: make it current first
     cudaDeviceSynchronize();
     return table_of(m, which, &rows);
+}
+
+int pda_adam_stats(pda_model* m, int64_t* out2, int reset) {
+    if (!m || !out2) return fail(PDA_ERR_ARG, "null argument");
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(out2, m->lazy_stats, 16, cudaMemcpyDeviceToHost));
+    if (reset) CK(cudaMemset(m->lazy_stats, 0, 16));
+    return PDA_OK;
 }
 
 int pda_set_adam_mode(pda_model* m, int mode) {
@@ -503,7 +514,7 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
     if (m->adam_lazy[0] || m->adam_lazy[1]) {   // rows of this batch replay the steps they skipped, before they are read
         LazyArgs la;
         lazy_args(m, &la);
-        ProfScope ps(m, PDA_PROF_ADAM, st);
+        ProfScope ps(m, PDA_PROF_ADAM_CATCHUP, st);
         if (launch_adam_lazy_rows(la, 0, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
     }
     s.pop_mode = m->cfg.train_mode == PDA_TRAIN_S_CONDITION ? 1 : m->cfg.train_mode == PDA_TRAIN_TEMP_POP ? 2 : 0;

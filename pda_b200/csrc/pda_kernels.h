@@ -49,6 +49,7 @@ struct LazyArgs {
     int64_t step_no;                            // steps applied so far = index of the current step
     const float* lr_hist;                       // lr_hist[s] = lr_t of step s (pointer already offset by the ring base)
     const float* pw; float lr;
+    unsigned long long* stats;                  // [0] rows updated with a gradient, [1] zero-gradient row-steps replayed
 };
 
 struct EvalArgs {

@@ -45,6 +45,9 @@ class DatasetApi_Model:
         self.Recommender = PDAModel(data_config['n_users'], data_config['n_items'], args.embed_size, train=args.train,
                                     batch_size=args.batch_size, lr=args.lr, regs=args.regs, device=device,
                                     seed=INIT_SEED, **kw)
+        adam_mode = os.environ.get("PDA_ADAM_MODE", "")     # "dense" | "lazy": same results bit for bit
+        if adam_mode and args.train != 'temp_pop':
+            self.Recommender.set_adam_mode(adam_mode)
         self.Recommender.set_train_csr(data.train_indptr, data.train_items, data.train_times,
                                        unique_times=data.unique_times or None)
         self.needs_reference_eval_batches = args.train == 'temp_pop'

@@ -76,10 +76,16 @@ class PDAModel:
         'lazy_users': lazy user table + dense item table (data-parallel item-gradient all-reduce)."""
         check(self.lib.pda_set_adam_mode(self._h, self.ADAM_MODES[mode]))
 
+    def adam_stats(self, reset=True):
+        """(rows updated with a gradient, zero-gradient row-steps replayed) by the lazy Adam kernels since the last reset."""
+        out = np.zeros(2, dtype=np.int64)
+        check(self.lib.pda_adam_stats(self._h, ptr(out), 1 if reset else 0))
+        return int(out[0]), int(out[1])
+
     def synchronize(self):
         check(self.lib.pda_synchronize(self._h))
 
-    PROF_KINDS = ("sampler", "bpr_step", "adam", "eval_exact", "eval_tensor")
+    PROF_KINDS = ("sampler", "bpr_step", "adam", "eval_exact", "eval_tensor", "adam_catchup")
 
     def profile(self, on=True):
         check(self.lib.pda_profile_enable(self._h, 1 if on else 0))
