@@ -118,7 +118,10 @@ def run_ours(a):
         a.gpus = world
     torch.cuda.set_device(local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # high-priority NCCL stream: the item-gradient all-reduce must get its CTAs although the (persistent, full-
+        # occupancy) Adam kernel of the rank-local half becomes runnable at the same instant
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=opts)
     dev = torch.device("cuda", local)
     pk = peaks()
     B, d = a.batch, a.dim

@@ -98,8 +98,8 @@ int pda_set_adam_powers(pda_model* m, const float* b1p_b2p_host);
 int pda_synchronize(pda_model* m);
 
 /* How the TF1 Adam sweep is evaluated.  TF1's Adam on IndexedSlices updates EVERY row at EVERY step (model_api.py:83 ->
- * AdamOptimizer._apply_sparse_shared).  PDA_ADAM_DENSE does exactly that sweep.  PDA_ADAM_LAZY (default for BPRMF /
- * PD / PDG) produces bit-identical tables without the sweep: a row replays the zero-gradient steps it skipped, in
+ * AdamOptimizer._apply_sparse_shared).  PDA_ADAM_DENSE does exactly that sweep (default while tables, slots
+ * and accumulators fit the L2: <= 256 MB).  PDA_ADAM_LAZY (default for larger BPRMF / PD / PDG models) produces bit-identical tables without the sweep: a row replays the zero-gradient steps it skipped, in
  * registers, with the same fp32 operations and the same per-step lr_t, when it is next sampled or when the tables
  * are read (eval, pda_get_table, ...).  PDA_ADAM_LAZY_USERS: lazy user table, dense item table (data-parallel runs whose
  * item gradient is all-reduced).  BPR(t)-pop always runs dense. */
@@ -174,6 +174,9 @@ void* pda_loss_acc_ptr(pda_model* m);
 int pda_forward_backward_device(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                                 const float* pos_pop, const float* neg_pop, int64_t B, void* stream);
 int pda_adam_apply(pda_model* m, void* stream);
+/* the same in two halves: part 1 = tables kept lazily (rank-local gradients; may run while the exchange of the other
+ * gradient is in flight), part 2 = dense sweep of the remaining variables + loss / beta-power bookkeeping; 3 = both */
+int pda_adam_apply_part(pda_model* m, int part, void* stream);
 int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                          const float* pos_pop, const float* neg_pop, int64_t B, void* stream);
 /* loss3 of the last enqueued step (synchronises `stream`) */

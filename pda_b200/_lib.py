@@ -62,6 +62,7 @@ PROTOTYPES = {
     "pda_loss_acc_ptr": (c_vp, [c_vp]),
     "pda_forward_backward_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp]),
     "pda_adam_apply": (C.c_int, [c_vp, c_vp]),
+    "pda_adam_apply_part": (C.c_int, [c_vp, C.c_int, c_vp]),
     "pda_stage_batch_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp]),
     "pda_read_loss": (C.c_int, [c_vp, c_vp, c_vp]),
     "pda_read_loss_sums": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),

@@ -162,7 +162,12 @@ int pda_create(const pda_config* cfg, pda_model** out) {
     for (int t = 0; t < 2; ++t) {
         CK(dmalloc(&m->applied[t], (size_t)m->rows[t])); CK(dmalloc(&m->stamp[t], (size_t)m->rows[t]));
         CK(cudaMemset(m->applied[t], 0, (size_t)m->rows[t] * 4)); CK(cudaMemset(m->stamp[t], 0, (size_t)m->rows[t] * 4));
-        m->adam_lazy[t] = cfg->train_mode == PDA_TRAIN_TEMP_POP ? 0 : 1;
+    }
+    {   // default: lazy replay when tables + slots + accumulators spill the 126 MB L2 (the dense sweep is then HBM
+        // traffic); small tables stay L2-resident and the plain sweep is faster (Douban: 0.1 s vs 0.3 s per epoch)
+        const double bytes = (double)(m->nU + m->nI) * m->d * 16.0;
+        const int lazy = cfg->train_mode != PDA_TRAIN_TEMP_POP && bytes > 256.0 * 1024 * 1024;
+        m->adam_lazy[0] = m->adam_lazy[1] = lazy;
     }
     CK(dmalloc(&m->lr_hist, (size_t)PDA_LR_CAP));
     CK(dmalloc(&m->lazy_stats, 2)); CK(cudaMemset(m->lazy_stats, 0, 16));
@@ -533,9 +538,12 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
 }
 
 // TF1 Adam sweep over both tables (one kernel) + loss / beta-power bookkeeping
-static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st) {
+// parts: 1 = the rank-local half (lazily maintained tables: their gradient never leaves the GPU),
+//        2 = the exchanged half (dense sweep of the remaining variables) + loss / beta-power bookkeeping, 3 = both.
+// Data-parallel callers run part 1 while the item-gradient all-reduce is in flight, then part 2.
+static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st, int parts = 3) {
     float* lr_slot = nullptr;
-    if (apply_adam) {
+    if (apply_adam && (parts & 1)) {
         const bool any_lazy = m->adam_lazy[0] || m->adam_lazy[1];
         if (any_lazy) {
             if (!m->cur_users) return fail(PDA_ERR_STATE, "pda_adam_apply without a preceding forward/backward");
@@ -544,6 +552,9 @@ static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st) {
             ProfScope ps(m, PDA_PROF_ADAM, st);
             if (launch_adam_lazy_rows(la, 1, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
         }
+    }
+    if (!(parts & 2)) return PDA_OK;
+    if (apply_adam) {
         AdamArgs a;
         memset(&a, 0, sizeof(a));
         bool any_dense = false;
@@ -604,6 +615,15 @@ int pda_forward_backward_device(pda_model* m, const int32_t* users, const int32_
     if (!pos || !neg) return fail(PDA_ERR_ARG, "null index pointer");
     if (m->cfg.train_mode == PDA_TRAIN_S_CONDITION && (!pp || !np_)) return fail(PDA_ERR_ARG, "s_condition needs pos_pop/neg_pop");
     int rc = enqueue_fwd_bwd(m, users, pos, neg, pp, np_, B, uniq, (cudaStream_t)stream);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+int pda_adam_apply_part(pda_model* m, int part, void* stream) {
+    if (!m || part < 1 || part > 3) return fail(PDA_ERR_ARG, "bad argument");
+    CK(cudaSetDevice(m->cfg.device));
+    int rc = enqueue_adam(m, true, (cudaStream_t)stream, part);
     if (rc) return rc;
     CK(cudaGetLastError());
     return PDA_OK;

@@ -240,8 +240,9 @@ class PDAModel:
         B = self.batch_size if B is None else int(B)
         check(self.lib.pda_forward_backward_device(self._h, None, None, None, None, None, B, ptr(stream) if stream else None))
 
-    def adam_apply(self, stream=0):
-        check(self.lib.pda_adam_apply(self._h, ptr(stream) if stream else None))
+    def adam_apply(self, stream=0, part=3):
+        """part 1: lazily kept (rank-local) tables; part 2: dense sweep of the rest + bookkeeping; 3: both."""
+        check(self.lib.pda_adam_apply_part(self._h, int(part), ptr(stream) if stream else None))
 
     def stage_batch(self, users, pos_items, neg_items, pos_pop=None, neg_pop=None, stream=0):
         u, p, n = _i32(users), _i32(pos_items), _i32(neg_items)

@@ -34,6 +34,7 @@ class ShardedTrainer:
         self.model, self.world, self.rank = model, int(world), int(rank)
         self._gi = self._acc = None
         self._reduce = reducer
+        self._async_reduce = None
         if self.world > 1:
             if hasattr(model, "set_adam_mode"):
                 # the item gradient is the sum over ranks: which item rows were touched is not known locally,
@@ -43,6 +44,8 @@ class ShardedTrainer:
             import torch.distributed as dist
             if reducer is None:
                 self._reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
+                if hasattr(model, "lib"):     # the GPU model: split optimizer + asynchronous NCCL work handles
+                    self._async_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
             if hasattr(model, "exchange_tensors"):     # host stand-ins (tests) hand their buffers over directly
                 self._gi, self._acc = model.exchange_tensors()
             else:
@@ -55,6 +58,20 @@ class ShardedTrainer:
         self._reduce(self._gi)     # dense item-gradient block, summed over ranks (NVLink / NVSwitch)
         self._reduce(self._acc)    # 2 doubles: loss partial sums -> global mean
 
+    def _exchange_and_apply(self, stream):
+        """item-gradient all-reduce overlapped with the rank-local half of the optimizer: the user table's gradient
+        never leaves the GPU, so its Adam update runs on the compute stream while NCCL moves the item gradient."""
+        m = self.model
+        if self._async_reduce is None:
+            self._exchange()
+            m.adam_apply(stream)
+            return
+        works = [self._async_reduce(self._gi), self._async_reduce(self._acc)]
+        m.adam_apply(stream, part=1)
+        for w in works:
+            w.wait()               # stream-level dependency, the host does not block
+        m.adam_apply(stream, part=2)
+
     def train_sampled(self, seed, epoch, step0, n_steps, B, stream=0):
         m = self.model
         if self.world == 1:
@@ -64,8 +81,7 @@ class ShardedTrainer:
         for k in range(n_steps):
             m.sample_batch(seed, epoch, step0 + k, B, stream, fetch=False)
             m.forward_backward_device(B, stream)
-            self._exchange()
-            m.adam_apply(stream)
+            self._exchange_and_apply(stream)
 
     def train_step_host(self, users, pos, neg, pos_pop=None, neg_pop=None, stream=0):
         m = self.model
@@ -74,6 +90,5 @@ class ShardedTrainer:
         m.set_global_batch(len(users) * self.world)
         B = m.stage_batch(users, pos, neg, pos_pop, neg_pop, stream)
         m.forward_backward_device(B, stream)
-        self._exchange()
-        m.adam_apply(stream)
+        self._exchange_and_apply(stream)
         return m.read_loss(stream)
