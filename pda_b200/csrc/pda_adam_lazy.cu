@@ -23,37 +23,10 @@
 
 namespace pda {
 
-__device__ __forceinline__ void adam_zero_grad_step(float& w, float& m, float& v, float lr_s) {
-    // adam_dense_kernel's update with g == 0: m*b1 + 0*omb1 == m*b1 and v*b2 + (0*0)*omb2 == v*b2 exactly
-    m = fmul(m, 0.9f);
-    v = fmul(v, 0.999f);
-    w = fsub(w, fdiv(fmul(lr_s, m), fadd(fsqrt(v), 1e-8f)));
-}
-
-__device__ __forceinline__ void adam_grad_step(float& w, float& m, float& v, float g, float lr_t) {
-    const float omb1 = fsub(1.0f, 0.9f), omb2 = fsub(1.0f, 0.999f);
-    m = fadd(fmul(m, 0.9f), fmul(g, omb1));
-    v = fadd(fmul(v, 0.999f), fmul(fmul(g, g), omb2));
-    w = fsub(w, fdiv(fmul(lr_t, m), fadd(fsqrt(v), 1e-8f)));
-}
-
-__device__ __forceinline__ void replay4(float4& w, float4& m, float4& v, const float* __restrict__ lr_hist, int64_t from,
-                                        int64_t to) {
-    if (m.x == 0.f && m.y == 0.f && m.z == 0.f && m.w == 0.f && v.x == 0.f && v.y == 0.f && v.z == 0.f && v.w == 0.f)
-        return;   // 0*b = 0 and 0/(0+eps) = 0: the identity
-    for (int64_t s = from; s < to; ++s) {
-        const float lr_s = __ldg(lr_hist + s);
-        adam_zero_grad_step(w.x, m.x, v.x, lr_s);
-        adam_zero_grad_step(w.y, m.y, v.y, lr_s);
-        adam_zero_grad_step(w.z, m.z, v.z, lr_s);
-        adam_zero_grad_step(w.w, m.w, v.w, lr_s);
-    }
-}
-
 // PHASE 0: catch-up to step t.  PHASE 1: apply step t with gradient.  One group of G lanes per batch entry
 // (entry e < B: user row, B <= e < 2B: pos item row, else neg item row), C float4 chunks per lane.
 template <int G, int C, int PHASE>
-__global__ void __launch_bounds__(256) adam_lazy_rows_kernel(LazyArgs a) {
+__global__ void __launch_bounds__(256, 6) adam_lazy_rows_kernel(LazyArgs a) {
     constexpr int GPW = 32 / G;
     const int lane = threadIdx.x & 31, gl = lane % G, gw = lane / G;
     const int64_t warp_global = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -67,8 +40,9 @@ __global__ void __launch_bounds__(256) adam_lazy_rows_kernel(LazyArgs a) {
         lr_t = fdiv(fmul(a.lr, fsqrt(fsub(1.0f, b2p))), fsub(1.0f, b1p));
     }
     const int64_t n_entries = 3 * a.B;
+    const int64_t e_begin = a.lazy[0] ? 0 : a.B;      // user entries are skipped when the step kernel owns the user rows
     unsigned long long stat = 0;   // per-lane tally, reduced once per warp at the end (one same-address atomic per warp)
-    for (int64_t base = warp_global * GPW; base < n_entries; base += n_warps * GPW) {
+    for (int64_t base = e_begin + warp_global * GPW; base < n_entries; base += n_warps * GPW) {
         const int64_t e = base + gw;
         const bool valid = e < n_entries;
         int tbl = 0;
@@ -97,7 +71,7 @@ __global__ void __launch_bounds__(256) adam_lazy_rows_kernel(LazyArgs a) {
                     if (ch < q) {
                         float4 w = *reinterpret_cast<float4*>(Wr + 4 * ch), m = *reinterpret_cast<float4*>(Mr + 4 * ch),
                                v = *reinterpret_cast<float4*>(Vr + 4 * ch);
-                        replay4(w, m, v, a.lr_hist, done, t);
+                        lazy_replay4(w, m, v, a.lr_hist, done, t);
                         *reinterpret_cast<float4*>(Wr + 4 * ch) = w;
                         *reinterpret_cast<float4*>(Mr + 4 * ch) = m;
                         *reinterpret_cast<float4*>(Vr + 4 * ch) = v;
@@ -114,10 +88,10 @@ __global__ void __launch_bounds__(256) adam_lazy_rows_kernel(LazyArgs a) {
                 if (ch < q) {
                     float4 w = *reinterpret_cast<float4*>(Wr + 4 * ch), m = *reinterpret_cast<float4*>(Mr + 4 * ch),
                            v = *reinterpret_cast<float4*>(Vr + 4 * ch), g = *reinterpret_cast<float4*>(Gr + 4 * ch);
-                    adam_grad_step(w.x, m.x, v.x, g.x, lr_t);
-                    adam_grad_step(w.y, m.y, v.y, g.y, lr_t);
-                    adam_grad_step(w.z, m.z, v.z, g.z, lr_t);
-                    adam_grad_step(w.w, m.w, v.w, g.w, lr_t);
+                    lazy_grad_step(w.x, m.x, v.x, g.x, lr_t);
+                    lazy_grad_step(w.y, m.y, v.y, g.y, lr_t);
+                    lazy_grad_step(w.z, m.z, v.z, g.z, lr_t);
+                    lazy_grad_step(w.w, m.w, v.w, g.w, lr_t);
                     *reinterpret_cast<float4*>(Wr + 4 * ch) = w;
                     *reinterpret_cast<float4*>(Mr + 4 * ch) = m;
                     *reinterpret_cast<float4*>(Vr + 4 * ch) = v;
@@ -146,7 +120,7 @@ int launch_adam_lazy_rows(const LazyArgs& a, int phase, cudaStream_t st) {
     const int C = (q + G - 1) / G;
     const int64_t warps_needed = (3 * a.B + (32 / G) - 1) / (32 / G);
     int64_t blocks = (warps_needed + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148 * 6) blocks = 148 * 6;      // one resident wave under the launch bounds
     if (blocks < 1) blocks = 1;
     const int grid = (int)blocks;
     switch (G) {
@@ -182,7 +156,7 @@ __global__ void __launch_bounds__(256) adam_lazy_flush_kernel(LazyArgs a, int tb
             for (int ch = lane; ch < q; ch += 32) {
                 float4 w = *reinterpret_cast<float4*>(Wr + 4 * ch), m = *reinterpret_cast<float4*>(Mr + 4 * ch),
                        v = *reinterpret_cast<float4*>(Vr + 4 * ch);
-                replay4(w, m, v, a.lr_hist, done, t);
+                lazy_replay4(w, m, v, a.lr_hist, done, t);
                 *reinterpret_cast<float4*>(Wr + 4 * ch) = w;
                 *reinterpret_cast<float4*>(Mr + 4 * ch) = m;
                 *reinterpret_cast<float4*>(Vr + 4 * ch) = v;

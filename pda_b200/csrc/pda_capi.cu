@@ -43,6 +43,7 @@ struct pda_model {
     int adam_lazy[2]; int32_t* applied[2]; int32_t* stamp[2];
     float* lr_hist; int64_t step_no, lr_base; unsigned long long* lazy_stats;
     const int32_t *cur_users, *cur_pos, *cur_neg; int64_t cur_B;   // batch of the step in flight
+    int cur_fused, fuse_user_adam;
     float* pw;          // {beta1_power, beta2_power}
     double* loss_acc;   // {sum log(sigmoid+1e-10), sum of squares}
     float* loss3;       // device {loss, mf, reg}
@@ -168,6 +169,8 @@ int pda_create(const pda_config* cfg, pda_model** out) {
         const double bytes = (double)(m->nU + m->nI) * m->d * 16.0;
         const int lazy = cfg->train_mode != PDA_TRAIN_TEMP_POP && bytes > 256.0 * 1024 * 1024;
         m->adam_lazy[0] = m->adam_lazy[1] = lazy;
+        const char* e = getenv("PDA_FUSE_USER_ADAM");
+        m->fuse_user_adam = e ? atoi(e) : 1;
     }
     CK(dmalloc(&m->lr_hist, (size_t)PDA_LR_CAP));
     CK(dmalloc(&m->lazy_stats, 2)); CK(cudaMemset(m->lazy_stats, 0, 16));
@@ -505,7 +508,7 @@ int pda_get_batch(pda_model* m, int64_t B, int32_t* users, int32_t* pos, int32_t
 
 // gather -> loss -> gradient scatter: ONE kernel (gradients land in the table-shaped accumulators G)
 static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
-                           const float* np_, int64_t B, int uniq, cudaStream_t st) {
+                           const float* np_, int64_t B, int uniq, cudaStream_t st, bool will_apply = true) {
     StepArgs s;
     memset(&s, 0, sizeof(s));
     s.U = m->W[0]; s.I = m->W[1]; s.GU = m->G[0]; s.GI = m->G[1];
@@ -516,11 +519,20 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
     s.invB = 1.0f / (float)m->last_B;
     s.loss_acc = m->loss_acc;
     m->cur_users = users; m->cur_pos = pos; m->cur_neg = neg; m->cur_B = B;
-    if (m->adam_lazy[0] || m->adam_lazy[1]) {   // rows of this batch replay the steps they skipped, before they are read
+    // distinct users + lazily kept user table + an Adam step that is certain to follow: the step kernel itself
+    // catches the user rows up and applies their update (bpr_step_kernel UMODE 2)
+    m->cur_fused = m->adam_lazy[0] && uniq && will_apply && m->fuse_user_adam;
+    if ((m->adam_lazy[0] && !m->cur_fused) || m->adam_lazy[1]) {   // rows of this batch replay the steps they skipped
         LazyArgs la;
         lazy_args(m, &la);
+        if (m->cur_fused) la.lazy[0] = 0;
         ProfScope ps(m, PDA_PROF_ADAM_CATCHUP, st);
         if (launch_adam_lazy_rows(la, 0, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
+    }
+    if (m->cur_fused) {
+        s.fuse_user_adam = 1; s.Uw = m->W[0]; s.MU = m->Mo[0]; s.VU = m->Vo[0]; s.appliedU = m->applied[0];
+        s.stampU = m->stamp[0]; s.lr_hist = m->lr_hist - m->lr_base; s.pw = m->pw; s.lr = m->cfg.lr; s.step_no = m->step_no;
+        s.stats = m->lazy_stats;
     }
     s.pop_mode = m->cfg.train_mode == PDA_TRAIN_S_CONDITION ? 1 : m->cfg.train_mode == PDA_TRAIN_TEMP_POP ? 2 : 0;
     s.uniq_users = uniq;
@@ -544,11 +556,12 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
 static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st, int parts = 3) {
     float* lr_slot = nullptr;
     if (apply_adam && (parts & 1)) {
-        const bool any_lazy = m->adam_lazy[0] || m->adam_lazy[1];
+        const bool any_lazy = (m->adam_lazy[0] && !m->cur_fused) || m->adam_lazy[1];
         if (any_lazy) {
             if (!m->cur_users) return fail(PDA_ERR_STATE, "pda_adam_apply without a preceding forward/backward");
             LazyArgs la;
             lazy_args(m, &la);
+            if (m->cur_fused) la.lazy[0] = 0;
             ProfScope ps(m, PDA_PROF_ADAM, st);
             if (launch_adam_lazy_rows(la, 1, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
         }
@@ -581,7 +594,7 @@ static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st, int part
 
 static int enqueue_step(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
                         const float* np_, int64_t B, int uniq, bool apply_adam, cudaStream_t st) {
-    int rc = enqueue_fwd_bwd(m, users, pos, neg, pp, np_, B, uniq, st);
+    int rc = enqueue_fwd_bwd(m, users, pos, neg, pp, np_, B, uniq, st, apply_adam);
     if (rc) return rc;
     return enqueue_adam(m, apply_adam, st);
 }
@@ -798,8 +811,8 @@ int pda_temp_item_bias_host(pda_model* m, int32_t first_user, float* out) {
 }
 
 // ---- recommendation ----
-// PDA_EVAL_AUTO: the tcgen05 filter when the shape supports it (d in {64,128}, >= 4096 items) and there are enough
-// rows to fill the machine, else the exact CUDA-core kernel.  Both give identical ids and scores.
+// PDA_EVAL_AUTO: the tcgen05 filter when the shape supports it (d in {64,128}, >= 4096 items; few rows are spread
+// over item-range splits), else the exact CUDA-core kernel.  Both give identical ids and scores.
 static int do_recommend(pda_model* m, const EvalArgs& a, int backend, cudaStream_t st) {
     flush_lazy(m, st);     // scoring reads both tables: rows that skipped Adam steps catch up first
     if (a.K < 1 || a.K > 128 || a.M < 1) return fail(PDA_ERR_ARG, "bad eval arguments (K in [1,128], M >= 1)");
@@ -807,7 +820,7 @@ static int do_recommend(pda_model* m, const EvalArgs& a, int backend, cudaStream
     if (backend == PDA_EVAL_TENSOR && !tc_ok)
         return fail(PDA_ERR_ARG, "tensor-core eval needs embed_size in {64,128}, n_items >= 4096 (got d=%d, n_items=%lld)", a.d,
                     (long long)a.N);
-    const bool use_tc = backend == PDA_EVAL_TENSOR || (backend == PDA_EVAL_AUTO && tc_ok && a.M >= 512);
+    const bool use_tc = backend == PDA_EVAL_TENSOR || (backend == PDA_EVAL_AUTO && tc_ok);
     if (!use_tc) {
         ProfScope ps(m, PDA_PROF_EVAL, st);
         if (launch_recommend_exact(a, st)) return fail(PDA_ERR_ARG, "bad eval arguments (K in [1,128], M >= 1)");

@@ -31,6 +31,9 @@ struct StepArgs {
     const float* ub; const float* ib;           // mode 2: user_temp_bias [n_users], item_temp_init_bias [n_items, T+1]
     float* Gub; float* Gib;
     int uniq_users;   // users distinct within the batch -> plain stores for the user rows
+    // fused lazy Adam on the user row (UMODE 2): see bpr_step_kernel
+    int fuse_user_adam; float* Uw; float* MU; float* VU; int32_t* appliedU; int32_t* stampU;
+    const float* lr_hist; const float* pw; float lr; int64_t step_no; unsigned long long* stats;
 };
 
 struct AdamArgs {

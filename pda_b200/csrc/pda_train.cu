@@ -4,6 +4,8 @@
 //   sampler   MF/train_new_api.py:260-288 (BPRMF), :366-412 (PD), :415-456 (BPR(t)-pop)
 //   step      MF/model_api.py:51-53 (gather), :102-121 (PD loss), :123-134 (BPRMF loss)
 //   optimizer MF/model_api.py:83,471 -> tf.train.AdamOptimizer on IndexedSlices (dense sweep)
+#include <stdlib.h>
+
 #include "pda_kernels.h"
 
 namespace pda {
@@ -124,9 +126,17 @@ void launch_sampler(SamplerArgs a, cudaStream_t st) {
 // user row takes a plain store then).  Loss terms: per-lane partials -> warp shuffle ->
 // one fp64 atomic pair per warp.
 // ------------------------------------------------------------------------------------------
-template <int G, int C, int MODE, bool UNIQ>
+// UMODE: how the user-row gradient leaves the kernel
+//   0  red.global.add into GU (users may repeat inside the batch)
+//   1  plain store into GU (users distinct: rd.sample)
+//   2  users distinct AND the user table is kept lazily: the warp that owns the triple owns the user row, so it
+//      replays the row's skipped zero-gradient Adam steps in registers BEFORE the dot products (pda_adam_lazy.cu),
+//      and applies this step's Adam update to the row right away -- no GU traffic, no separate catch-up / apply
+//      pass over the user table.  Same fp32 operations in the same order as the separate kernels: bit-identical.
+template <int G, int C, int MODE, int UMODE>
 __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
     constexpr bool POP = MODE == 1, TEMP = MODE == 2;
+    constexpr bool UNIQ = UMODE >= 1, FUSE = UMODE == 2;
     constexpr int GPW = 32 / G;  // triples per warp per iteration
     const int lane = threadIdx.x & 31;
     const int gl = lane % G;       // lane within the group
@@ -136,6 +146,9 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
     const int q = a.d >> 2;  // float4 chunks per row
 
     double mf_acc = 0.0, sq_acc = 0.0;
+    unsigned long long n_replayed = 0;
+    float lr_t = 0.f;
+    if (FUSE) lr_t = fdiv(fmul(a.lr, fsqrt(fsub(1.0f, a.pw[1]))), fsub(1.0f, a.pw[0]));
 
     for (int64_t base = warp_global * GPW; base < a.B; base += n_warps * GPW) {
         const int64_t i = base + gw;
@@ -160,13 +173,32 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
         const float* pr = a.I + (int64_t)ip * a.d;
         const float* nr = a.I + (int64_t)in * a.d;
         float4 u[C], p[C], n[C];
+        float4 mu[FUSE ? C : 1], vu[FUSE ? C : 1];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int ch = gl + G * c;
             if (valid && ch < q) {
-                u[c] = ldg_f4(ur + 4 * ch); p[c] = ldg_f4(pr + 4 * ch); n[c] = ldg_f4(nr + 4 * ch);
+                if (FUSE) {   // the row is rewritten below: plain (coherent) loads
+                    u[c] = *reinterpret_cast<const float4*>(ur + 4 * ch);
+                    mu[c] = *reinterpret_cast<const float4*>(a.MU + (int64_t)iu * a.d + 4 * ch);
+                    vu[c] = *reinterpret_cast<const float4*>(a.VU + (int64_t)iu * a.d + 4 * ch);
+                } else {
+                    u[c] = ldg_f4(ur + 4 * ch);
+                }
+                p[c] = ldg_f4(pr + 4 * ch); n[c] = ldg_f4(nr + 4 * ch);
             } else {
                 u[c] = p[c] = n[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (FUSE) mu[c] = vu[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (FUSE && valid) {
+            // catch up: zero-gradient steps applied[u] .. step_no-1 (a never-touched row has m = v = 0: identity)
+            const int64_t done = a.appliedU[iu];
+            if (done < a.step_no && a.stampU[iu] != 0) {
+                if (gl == 0) n_replayed += (unsigned long long)(a.step_no - done);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (gl + G * c < q) lazy_replay4(u[c], mu[c], vu[c], a.lr_hist, done, a.step_no);
             }
         }
         float sp = 0.0f, sn = 0.0f, sq = 0.0f;
@@ -231,13 +263,26 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
                     dnv.y = fadd(fmul(cn, u[c].y), fmul(a.lb, n[c].y));
                     dnv.z = fadd(fmul(cn, u[c].z), fmul(a.lb, n[c].z));
                     dnv.w = fadd(fmul(cn, u[c].w), fmul(a.lb, n[c].w));
-                    if (UNIQ) *reinterpret_cast<float4*>(gu + 4 * ch) = du;
+                    if (FUSE) {
+                        float4 w = u[c];
+                        lazy_grad_step(w.x, mu[c].x, vu[c].x, du.x, lr_t); lazy_grad_step(w.y, mu[c].y, vu[c].y, du.y, lr_t);
+                        lazy_grad_step(w.z, mu[c].z, vu[c].z, du.z, lr_t); lazy_grad_step(w.w, mu[c].w, vu[c].w, du.w, lr_t);
+                        *reinterpret_cast<float4*>(a.Uw + (int64_t)iu * a.d + 4 * ch) = w;
+                        *reinterpret_cast<float4*>(a.MU + (int64_t)iu * a.d + 4 * ch) = mu[c];
+                        *reinterpret_cast<float4*>(a.VU + (int64_t)iu * a.d + 4 * ch) = vu[c];
+                    } else if (UNIQ) *reinterpret_cast<float4*>(gu + 4 * ch) = du;
                     else red_add_f4(gu + 4 * ch, du);
                     red_add_f4(gp + 4 * ch, dpv);
                     red_add_f4(gn + 4 * ch, dnv);
                 }
             }
+            if (FUSE && gl == 0) { a.appliedU[iu] = (int32_t)(a.step_no + 1); a.stampU[iu] = 1; }
         }
+    }
+    if (FUSE) {
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) n_replayed += __shfl_xor_sync(0xffffffffu, n_replayed, off);
+        if (lane == 0 && n_replayed) atomicAdd(a.stats + 1, n_replayed);
     }
     // loss partials: warp reduce, one fp64 atomic pair per warp
 #pragma unroll
@@ -254,14 +299,16 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
 template <int G, int C>
 static void launch_step_gc(const StepArgs& a, int grid, cudaStream_t st) {
     if (a.pop_mode == 1) {
-        if (a.uniq_users) bpr_step_kernel<G, C, 1, true><<<grid, 256, 0, st>>>(a);
-        else bpr_step_kernel<G, C, 1, false><<<grid, 256, 0, st>>>(a);
+        if (a.uniq_users && a.fuse_user_adam) bpr_step_kernel<G, C, 1, 2><<<grid, 256, 0, st>>>(a);
+        else if (a.uniq_users) bpr_step_kernel<G, C, 1, 1><<<grid, 256, 0, st>>>(a);
+        else bpr_step_kernel<G, C, 1, 0><<<grid, 256, 0, st>>>(a);
     } else if (a.pop_mode == 2) {
-        if (a.uniq_users) bpr_step_kernel<G, C, 2, true><<<grid, 256, 0, st>>>(a);
-        else bpr_step_kernel<G, C, 2, false><<<grid, 256, 0, st>>>(a);
+        if (a.uniq_users) bpr_step_kernel<G, C, 2, 1><<<grid, 256, 0, st>>>(a);
+        else bpr_step_kernel<G, C, 2, 0><<<grid, 256, 0, st>>>(a);
     } else {
-        if (a.uniq_users) bpr_step_kernel<G, C, 0, true><<<grid, 256, 0, st>>>(a);
-        else bpr_step_kernel<G, C, 0, false><<<grid, 256, 0, st>>>(a);
+        if (a.uniq_users && a.fuse_user_adam) bpr_step_kernel<G, C, 0, 2><<<grid, 256, 0, st>>>(a);
+        else if (a.uniq_users) bpr_step_kernel<G, C, 0, 1><<<grid, 256, 0, st>>>(a);
+        else bpr_step_kernel<G, C, 0, 0><<<grid, 256, 0, st>>>(a);
     }
 }
 
@@ -271,10 +318,12 @@ int launch_bpr_step(const StepArgs& a, cudaStream_t st) {
     int G = 1;
     while (G < q && G < 32) G *= 2;
     const int C = (q + G - 1) / G;
-    // grid: enough warps to cover the batch once, capped at 8 resident CTAs x 148 SMs
+    // grid: enough warps to cover the batch once, capped at 8 CTAs x 148 SMs (grid-stride beyond that)
+    static int per_sm = 0;
+    if (!per_sm) { const char* e = getenv("PDA_STEP_GRID_PER_SM"); per_sm = e ? atoi(e) : 8; if (per_sm < 1) per_sm = 8; }
     int64_t warps_needed = (a.B + (32 / G) - 1) / (32 / G);
     int64_t blocks = (warps_needed + 7) / 8;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks > 148 * per_sm) blocks = 148 * per_sm;
     if (blocks < 1) blocks = 1;
     const int grid = (int)blocks;
     switch (G) {
