@@ -246,7 +246,12 @@ def run_ours(a):
     cat_ms, cat_n = prof["adam_catchup"]
     samp_ms, samp_n = prof["sampler"]
     bytes_triple = 24 * d + 20
-    step_gbs = bytes_triple * B / (step_ms / max(step_n, 1) * 1e-3) / 1e9 if step_ms > 0 else 0.0
+    # lazy mode + distinct users (device sampler): the step kernel also owns the Adam update of its B user rows
+    # (catch-up replay + apply) -> its algorithmic bytes are SURVEY 8d's step figure PLUS SURVEY 8d's
+    # Adam-apply figure (rows x d x 4 x 6) for those B rows; the separate apply kernel then covers item rows only
+    fused = a.adam == "lazy" and os.environ.get("PDA_FUSE_USER_ADAM", "1") != "0"
+    step_bytes = bytes_triple * B + (B * d * 4 * 6 if fused else 0)
+    step_gbs = step_bytes / (step_ms / max(step_n, 1) * 1e-3) / 1e9 if step_ms > 0 else 0.0
     if a.adam == "dense" or world > 1:
         adam_rows = (0 if (a.adam == "lazy") else users_local) + a.items      # rows swept per step
         adam_rows += rows_updated / max(a.steps, 1)
@@ -256,7 +261,9 @@ def run_ours(a):
     adam_gbs = adam_bytes / (adam_ms / max(a.steps, 1) * 1e-3) / 1e9 if adam_ms > 0 else 0.0
     kern = {
         "bpr_step": {"ms_per_launch": step_ms / max(step_n, 1), "share_of_step": step_ms / ms, "achieved": step_gbs,
-                     "frac": step_gbs / pk["hbm"], "algorithmic_bytes": bytes_triple * B, "unit": "GB/s"},
+                     "frac": step_gbs / pk["hbm"], "algorithmic_bytes": step_bytes, "unit": "GB/s",
+                     "bytes_model": "B*(24d+20)" + (" + B*d*4*6 (fused Adam of the B distinct user rows)" if fused else ""),
+                     "bpr_only_gbs": bytes_triple * B / (step_ms / max(step_n, 1) * 1e-3) / 1e9 if step_ms > 0 else 0.0},
         "adam_apply": {"ms_per_step": adam_ms / max(a.steps, 1), "launches_per_step": adam_n / max(a.steps, 1),
                        "share_of_step": adam_ms / ms, "achieved": adam_gbs, "frac": adam_gbs / pk["hbm"],
                        "algorithmic_bytes": adam_bytes, "rows_per_step": adam_rows, "mode": a.adam, "unit": "GB/s"},

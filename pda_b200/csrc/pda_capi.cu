@@ -44,6 +44,7 @@ struct pda_model {
     float* lr_hist; int64_t step_no, lr_base; unsigned long long* lazy_stats;
     const int32_t *cur_users, *cur_pos, *cur_neg; int64_t cur_B;   // batch of the step in flight
     int cur_fused, fuse_user_adam;
+    int32_t* seen; int32_t seen_tag;   // scratch of the distinct-users check of host batches
     float* pw;          // {beta1_power, beta2_power}
     double* loss_acc;   // {sum log(sigmoid+1e-10), sum of squares}
     float* loss3;       // device {loss, mf, reg}
@@ -192,7 +193,7 @@ void pda_destroy(pda_model* m) {
     cudaDeviceSynchronize();
     for (int t = 0; t < 4; ++t) { cudaFree(m->W[t]); cudaFree(m->Mo[t]); cudaFree(m->Vo[t]); cudaFree(m->G[t]); }
     for (int t = 0; t < 2; ++t) { cudaFree(m->applied[t]); cudaFree(m->stamp[t]); }
-    cudaFree(m->lr_hist); cudaFree(m->lazy_stats);
+    cudaFree(m->lr_hist); cudaFree(m->lazy_stats); cudaFree(m->seen);
     cudaFree(m->pw); cudaFree(m->loss_acc); cudaFree(m->loss3); cudaFree(m->loss_sum); cudaFreeHost(m->loss3_pinned);
     cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
     cudaFree(m->pop_train);
@@ -719,7 +720,20 @@ int pda_train_step_host(pda_model* m, const int32_t* users, const int32_t* pos, 
     CK(cudaSetDevice(m->cfg.device));
     int rc = stage_batch(m, users, pos, neg, pp, np_, B, 0);
     if (rc) return rc;
-    rc = enqueue_step(m, m->b_users, m->b_pos, m->b_neg, m->b_pp, m->b_np, B, 0, true, 0);
+    // The reference's batches hold distinct users (rd.sample, train_new_api.py:384-385) but a host caller may pass
+    // anything: check on the device (one pass over B ids, ~50 us at B = 2^20) whether the fused user-row path applies.
+    int uniq = 0;
+    if (m->adam_lazy[0] && m->fuse_user_adam) {
+        if (!m->seen) { CK(dmalloc(&m->seen, (size_t)m->nU + 1)); CK(cudaMemset(m->seen, 0, ((size_t)m->nU + 1) * 4)); }
+        int32_t* dup = m->seen + m->nU;
+        CK(cudaMemsetAsync(dup, 0, 4, 0));
+        launch_users_distinct(m->b_users, B, m->seen, ++m->seen_tag, dup, 0);
+        int32_t* hdup = (int32_t*)((char*)m->loss3_pinned + 56);
+        CK(cudaMemcpyAsync(hdup, dup, 4, cudaMemcpyDeviceToHost, 0));
+        CK(cudaStreamSynchronize(0));
+        uniq = *hdup == 0;
+    }
+    rc = enqueue_step(m, m->b_users, m->b_pos, m->b_neg, m->b_pp, m->b_np, B, uniq, true, 0);
     if (rc) return rc;
     CK(cudaMemcpyAsync(m->loss3_pinned, m->loss3, 12, cudaMemcpyDeviceToHost, 0));
     CK(cudaStreamSynchronize(0));

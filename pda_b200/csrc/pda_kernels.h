@@ -84,6 +84,7 @@ void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float*
                         int batch_size, int advance_powers, float lr, float* lr_slot, cudaStream_t st);
 int launch_adam_lazy_rows(const LazyArgs& a, int phase, cudaStream_t st);
 void launch_adam_lazy_flush(const LazyArgs& a, int tbl, int64_t n_rows, cudaStream_t st);
+void launch_users_distinct(const int32_t* users, int64_t B, int32_t* seen, int32_t tag, int32_t* dup, cudaStream_t st);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t value, cudaStream_t st);
 void launch_f32_to_i32(const float* src, int32_t* dst, int64_t n, int32_t max_value, cudaStream_t st);
 void launch_temp_item_bias(const float* ub, const float* ib, int64_t n_items, int temp_num, int32_t first_user,

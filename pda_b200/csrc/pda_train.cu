@@ -387,6 +387,21 @@ void launch_adam_dense(const AdamArgs& a, cudaStream_t st) {
 }
 
 // loss3 = {loss, mf, reg}; beta powers advance (AdamOptimizer._finish); accumulators reset.
+// are the users of a host batch distinct (rd.sample)?  seen[] is an n_users scratch array of tags; a repeated user
+// finds this call's tag already there.  *dup is set to 1 when any user repeats.
+__global__ void users_distinct_kernel(const int32_t* __restrict__ users, int64_t B, int32_t* __restrict__ seen, int32_t tag,
+                                      int32_t* dup) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x)
+        if (atomicExch(seen + users[i], tag) == tag) *dup = 1;
+}
+
+void launch_users_distinct(const int32_t* users, int64_t B, int32_t* seen, int32_t tag, int32_t* dup, cudaStream_t st) {
+    int64_t blocks = (B + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    users_distinct_kernel<<<(int)blocks, 256, 0, st>>>(users, B, seen, tag, dup);
+}
+
 __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t value) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = value;
 }
