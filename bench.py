@@ -48,7 +48,7 @@ def parse_args():
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-steps", type=int, default=3)
-    ap.add_argument("--adam", default="lazy", choices=["lazy", "dense"],
+    ap.add_argument("--adam", default="auto", choices=["auto", "lazy", "lazy_users", "dense"],
                     help="how the TF1 every-row Adam sweep is evaluated (bit-identical results; see DESIGN.md 5.2)")
     return ap.parse_args()
 
@@ -135,8 +135,10 @@ def run_ours(a):
     model.set_train_csr_device(wrap_ptr(ds["indptr"]), wrap_ptr(ds["items"]), wrap_ptr(ds["times"]), ds["nnz"],
                                wrap_ptr(ds["active"]), ds["active"].numel(), unique_times=np.arange(ds["n_stages"] - 1))
     model.set_train_pop(P.cpu().numpy())
-    if a.adam == "dense":
-        model.set_adam_mode("dense")
+    if a.adam != "auto":
+        model.set_adam_mode(a.adam)
+    else:
+        a.adam = "lazy_users"    # what the library picks here: 10M user rows vs 2^20 refs/step -> lazy; 1M item rows vs 2^21 -> dense
     trainer = ShardedTrainer(model, world, rank)      # world > 1: lazy user table + dense (all-reduced) item table
     stream = torch.cuda.current_stream().cuda_stream
 
@@ -153,7 +155,7 @@ def run_ours(a):
     run_steps(0, a.warmup)
     barrier()
     model.profile(True)
-    if a.adam == "lazy":
+    if a.adam != "dense":
         model.adam_stats(reset=True)
     clocks = ClockSampler(local)
     if rank == 0:
@@ -169,7 +171,7 @@ def run_ours(a):
         clocks.stop()
     prof = model.profile_read()
     model.profile(False)
-    rows_updated, row_steps_replayed = model.adam_stats(reset=True) if a.adam == "lazy" else (0, 0)
+    rows_updated, row_steps_replayed = model.adam_stats(reset=True) if a.adam != "dense" else (0, 0)
     loss = model.read_loss(stream)
     t = torch.tensor([ms], device=dev, dtype=torch.float64)
     if world > 1:
@@ -249,14 +251,15 @@ def run_ours(a):
     # lazy mode + distinct users (device sampler): the step kernel also owns the Adam update of its B user rows
     # (catch-up replay + apply) -> its algorithmic bytes are SURVEY 8d's step figure PLUS SURVEY 8d's
     # Adam-apply figure (rows x d x 4 x 6) for those B rows; the separate apply kernel then covers item rows only
-    fused = a.adam == "lazy" and os.environ.get("PDA_FUSE_USER_ADAM", "1") != "0"
+    fused = a.adam in ("lazy", "lazy_users") and os.environ.get("PDA_FUSE_USER_ADAM", "1") != "0"
     step_bytes = bytes_triple * B + (B * d * 4 * 6 if fused else 0)
     step_gbs = step_bytes / (step_ms / max(step_n, 1) * 1e-3) / 1e9 if step_ms > 0 else 0.0
-    if a.adam == "dense" or world > 1:
-        adam_rows = (0 if (a.adam == "lazy") else users_local) + a.items      # rows swept per step
-        adam_rows += rows_updated / max(a.steps, 1)
-    else:
-        adam_rows = rows_updated / max(a.steps, 1)                           # rows updated with a gradient per step
+    # rows the Adam kernels outside the step kernel handle per step: dense-swept tables + lazily updated rows
+    adam_rows = rows_updated / max(a.steps, 1)
+    if a.adam == "dense":
+        adam_rows += users_local + a.items
+    elif a.adam == "lazy_users" or world > 1:
+        adam_rows += a.items
     adam_bytes = adam_rows * d * 4 * 6                                       # W, m, v read + written
     adam_gbs = adam_bytes / (adam_ms / max(a.steps, 1) * 1e-3) / 1e9 if adam_ms > 0 else 0.0
     kern = {

@@ -165,11 +165,14 @@ int pda_create(const pda_config* cfg, pda_model** out) {
         CK(dmalloc(&m->applied[t], (size_t)m->rows[t])); CK(dmalloc(&m->stamp[t], (size_t)m->rows[t]));
         CK(cudaMemset(m->applied[t], 0, (size_t)m->rows[t] * 4)); CK(cudaMemset(m->stamp[t], 0, (size_t)m->rows[t] * 4));
     }
-    {   // default: lazy replay when tables + slots + accumulators spill the 126 MB L2 (the dense sweep is then HBM
-        // traffic); small tables stay L2-resident and the plain sweep is faster (Douban: 0.1 s vs 0.3 s per epoch)
+    {   // default per table: the lazy replay pays off when (a) tables + slots + accumulators spill the 126 MB L2 (the
+        // dense sweep is then HBM traffic; small tables stay L2-resident: Douban 0.1 s vs 0.3 s per epoch) and (b) a step
+        // touches a small part of the table (rows > 4 x row references per step); a table that is mostly touched
+        // every step (1M items vs 2 x 2^20 item references) is swept densely at less traffic than catch-up + apply.
         const double bytes = (double)(m->nU + m->nI) * m->d * 16.0;
-        const int lazy = cfg->train_mode != PDA_TRAIN_TEMP_POP && bytes > 256.0 * 1024 * 1024;
-        m->adam_lazy[0] = m->adam_lazy[1] = lazy;
+        const bool big = cfg->train_mode != PDA_TRAIN_TEMP_POP && bytes > 256.0 * 1024 * 1024;
+        m->adam_lazy[0] = big && m->nU > 4 * m->cap;
+        m->adam_lazy[1] = big && m->nI > 8 * m->cap;
         const char* e = getenv("PDA_FUSE_USER_ADAM");
         m->fuse_user_adam = e ? atoi(e) : 1;
     }
