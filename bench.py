@@ -47,7 +47,7 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-eval", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--cpu-steps", type=int, default=10, help="steps of the cpu_baseline leg (about 0.4 s each on 16 cores)")
     ap.add_argument("--adam", default="auto", choices=["auto", "lazy", "lazy_users", "dense"],
                     help="how the TF1 every-row Adam sweep is evaluated (bit-identical results; see DESIGN.md 5.2)")
     return ap.parse_args()
@@ -101,6 +101,16 @@ class ClockSampler:
 
 def wrap_ptr(t):
     return int(t.data_ptr())
+
+
+def make_config(a, world):
+    """identical for our arm and the reference arm (the driver compares the two lines)"""
+    users_local = a.users // world
+    return {"workload": f"synthetic {a.users} users x {a.items} items d={a.dim}, PD (s_condition) gamma={GAMMA}, "
+                        f"TF1 every-row Adam semantics, B={a.batch} triples/step/GPU",
+            "users": a.users, "items": a.items, "d": a.dim, "batch_per_gpu": a.batch, "global_batch": a.batch * world,
+            "parallelism": f"user-shard x{world}, items replicated" + (" + NCCL item-grad allreduce" if world > 1 else ""),
+            "l2_policy": "tables >> L2 (user table %.1f GB per rank): no flush needed" % (users_local * a.dim * 4 / 1e9)}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -286,11 +296,7 @@ def run_ours(a):
         out = {"metric": "bpr_triples_per_sec", "value": value, "unit": "triples/s", "n_gpus": world, "steps": a.steps,
                "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-               "config": {"workload": f"synthetic {a.users} users x {a.items} items d={d}, PD (s_condition) gamma={GAMMA}, "
-                                      f"TF1 every-row Adam semantics ({a.adam} evaluation), B={B} triples/step/GPU",
-                          "users": a.users, "items": a.items, "d": d, "batch_per_gpu": B, "global_batch": B * world,
-                          "parallelism": f"user-shard x{world}, items replicated" + (" + NCCL item-grad allreduce" if world > 1 else ""),
-                          "l2_policy": "tables >> L2 (user table %.1f GB per rank)" % (users_local * d * 4 / 1e9)},
+               "config": dict(make_config(a, world), adam_evaluation=a.adam),
                "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e, "eval": ev,
                "gpu_launches": int(step_n + adam_n + cat_n + samp_n + a.steps), "clocks": clocks.summary(),
                "last_loss": [float(x) for x in loss]}
@@ -339,14 +345,12 @@ def run_reference(a):
     users_local = a.users // world
     ds = synth.make_synthetic(users_local, a.items, seed=SEED_DATA, device=dev)
     P = synth.train_pop_matrix_torch(ds["pop"], GAMMA)
-    steps = max(1, min(a.steps, a.cpu_steps))
+    steps = max(1, min(a.steps, 25))          # 25 x ~0.4 s: the whole arm ends within a minute
     cpu = cpu_baseline(a, ds, P, users_local, steps=steps)
     out = {"impl": "reference", "metric": "bpr_triples_per_sec", "value": cpu["value"], "unit": "triples/s",
            "n_gpus": a.gpus, "steps": steps, "warmup": 1, "ms_per_step": cpu["ms_per_step"], "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"synthetic {a.users} users x {a.items} items d={a.dim}, PD (s_condition) gamma={GAMMA}, "
-                                  f"TF1-dense Adam, B={a.batch} triples/step", "users": a.users, "items": a.items,
-                      "d": a.dim, "batch_per_gpu": a.batch},
+           "config": dict(make_config(a, world), adam_evaluation="dense (the reference's own sweep)"),
            "cpu_baseline": cpu,
            "e2e": {"value": cpu["value"], "unit": "triples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
