@@ -37,7 +37,10 @@ namespace pda {
 namespace tc {
 
 constexpr int TM = 128, TN = 256, KB = 64;          // CTA tile, K block (64 bf16 = one 128 B swizzle row)
-constexpr int NT = 384;                             // 12 warps: 0 TMA, 1 MMA, 2-3 idle, 4-11 epilogue
+constexpr int EPI_G = 2;                            // epilogue warp groups: each owns TN / EPI_G columns of every tile (4 measured no faster)
+constexpr int EPI_COLS = TN / EPI_G;                // columns per thread and tile, in chunks of 32
+constexpr int EPI_CH = EPI_COLS / 32;
+constexpr int NT = 128 + 128 * EPI_G;               // warps: 0 TMA, 1 MMA, 2-3 idle, then 4 * EPI_G epilogue warps
 constexpr int CHUNK = 32;
 
 // ------------------------------------------------------------------------------------------------------------
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 8); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4 * EPI_G); }
         mbar_init(bar_afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -260,9 +263,9 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread = (row 32q + lane, column half h) =====
+        // ===== epilogue: thread = (row 32q + lane, column group h of EPI_COLS columns) =====
         const int q = warp & 3, h = (warp - 4) >> 2;
-        const int e = (warp - 4) * 32 + lane;                    // 0..255: column slot for staging scol
+        const int e = (warp - 4) * 32 + lane;                    // epilogue thread index; the first 256 stage scol
         const int64_t row = (int64_t)m_tile * TM + 32 * q + lane;
         const bool row_ok = row < a.M;
         const float un = a.unorm[row] * a.c_err;
@@ -270,40 +273,42 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
         float tau = 0.f;
         if (PASS == 1) tau = row_ok ? a.tau[row] : INFINITY;
         // pass B: this thread owns segment (split, h) of its row's candidate list -> no atomics
-        const int seg = blockIdx.y * 2 + h;
+        const int seg = blockIdx.y * EPI_G + h;
         int32_t* my_cand = PASS == 1 ? a.cand + ((int64_t)row * a.n_seg + seg) * a.seg_cap : nullptr;
         int n_local = 0;
-        const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * 128);
+        const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * EPI_COLS);
         for (int i = 0; i < n_my; ++i) {
             const int t = t_first + i * step;
             const int acc = i & 1, aph = (i >> 1) & 1;
             const int64_t j0 = (int64_t)t * TN;
-            const float* sc = scol + acc * 256 + h * 128;
+            const float* sc = scol + acc * 256 + h * EPI_COLS;
             if (use_col) {
-                const int64_t j = j0 + e;
-                scol[acc * 256 + e] = j < a.N ? __ldg(a.col + j) : 0.f;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
+                if (e < TN) {
+                    const int64_t j = j0 + e;
+                    scol[acc * 256 + e] = j < a.N ? __ldg(a.col + j) : 0.f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_G) : "memory");
             }
             const float er = un * __ldg(a.tile_inorm + t);       // |s - s_lp| <= er for every item of this tile
             mbar_wait(bar_tfull + 8 * acc, aph);
             fence_after();
             uint32_t va[32], vb[32];
-            float bests[4];
+            float bests[EPI_CH];
             const uint32_t tbase = lane_base + (uint32_t)(acc * TN);
             tmem_ld32(tbase, va);
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
+            for (int cc = 0; cc < EPI_CH; ++cc) {
                 uint32_t* v = (cc & 1) ? vb : va;
                 tmem_ld_wait();
-                if (cc < 3) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), (cc & 1) ? va : vb);   // next chunk in flight
+                if (cc < EPI_CH - 1) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), (cc & 1) ? va : vb);   // next chunk in flight
                 else {
-                    // all four chunks are in registers: hand the accumulator stage back to the MMA warp
+                    // all chunks are in registers: hand the accumulator stage back to the MMA warp
                     fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
                 }
                 const int cb = cc * 32;                          // first column of this chunk inside this thread's half
-                const int64_t jb = j0 + h * 128 + cb;
+                const int64_t jb = j0 + h * EPI_COLS + cb;
                 if (PASS == 0) {
                     float best = -INFINITY;
                     if (jb + 32 <= a.N) {
@@ -387,9 +392,12 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                     }
                 }
             }
-            if (PASS == 0)   // this thread's four chunk maxima of the tile: one 16 B store, row-major [row][n_c]
-                *reinterpret_cast<float4*>(a.cmax + (int64_t)row * a.n_c + (t / a.se) * 8 + h * 4) =
-                    make_float4(bests[0], bests[1], bests[2], bests[3]);
+            if (PASS == 0) {   // this thread's chunk maxima of the tile: one vector store, row-major [row][n_c]
+                float* dst = a.cmax + (int64_t)row * a.n_c + (t / a.se) * 8 + h * EPI_CH;
+                if (EPI_CH == 4) *reinterpret_cast<float4*>(dst) = make_float4(bests[0], bests[1], bests[EPI_CH - 2], bests[EPI_CH - 1]);
+                else if (EPI_CH == 2) *reinterpret_cast<float2*>(dst) = make_float2(bests[0], bests[1]);
+                else dst[0] = bests[0];
+            }
         }
         if (PASS == 1) a.cnt[(int64_t)row * a.n_seg + seg] = n_local;
     }
@@ -588,7 +596,7 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
         const int64_t lo = a.mask_indptr[u], hi = a.mask_indptr[u + 1];
         for (int64_t z = lo + lane; z < hi; z += 32) {
             const int32_t it = __ldg(a.mask_items + z);
-            const int sg = (it / tc::TN / a.tiles_per_split) * 2 + ((it % tc::TN) >> 7);
+            const int sg = (it / tc::TN / a.tiles_per_split) * tc::EPI_G + (it % tc::TN) / tc::EPI_COLS;
             const int send = soff[sg + 1];
             int l = soff[sg], r = send;
             while (l < r) {
@@ -741,8 +749,8 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->tiles_per_split = (p->n_tiles + splits - 1) / splits;
     p->tiles_per_split = (p->tiles_per_split + se - 1) / se * se;    // splits start on sampled tiles
     p->splits = (p->n_tiles + p->tiles_per_split - 1) / p->tiles_per_split;
-    // candidate lists: one segment per (item split, column half); twice the expected total as head-room
-    p->n_seg = p->splits * 2;
+    // candidate lists: one segment per (item split, column group); twice the expected total as head-room
+    p->n_seg = p->splits * EPI_G;
     const int cap_total = a.N <= 262144 ? 1024 : 4096;
     p->seg_cap = ((2 * cap_total + p->n_seg - 1) / p->n_seg + 31) / 32 * 32;
     if (p->seg_cap < 64) p->seg_cap = 64;
