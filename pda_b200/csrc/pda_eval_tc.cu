@@ -36,7 +36,8 @@ namespace pda {
 
 namespace tc {
 
-constexpr int TM = 128, TN = 256, KB = 64;          // CTA tile, K block (64 bf16 = one 128 B swizzle row)
+constexpr int TM = 128, TN = 256, KB = 64;          // UMMA tile, K block (64 bf16 = one 128 B swizzle row)
+constexpr int MR = 2;                               // user tiles resident per CTA: every B tile from L2 serves MR * 128 users
 constexpr int EPI_G = 2;                            // epilogue warp groups: each owns TN / EPI_G columns of every tile (4 measured no faster)
 constexpr int EPI_COLS = TN / EPI_G;                // columns per thread and tile, in chunks of 32
 constexpr int EPI_CH = EPI_COLS / 32;
@@ -110,6 +111,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+// 1.0f if a >= b else 0.0f (FSET): the compare result as a float, so the hit mask can be accumulated with FFMAs on
+// the FMA pipe instead of SEL / IADD3 on the half-rate ALU pipe
+__device__ __forceinline__ float fset_ge(float a, float b) {
+    float d;
+    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
 
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1, layout type 2.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -148,12 +161,14 @@ __global__ void __launch_bounds__(256) tc_convert_rows_kernel(const float* __res
     if (lane == 0) norm[r] = sqrtf(sq) * 1.00001f;
 }
 
-__global__ void __launch_bounds__(256) tc_tile_norm_kernel(const float* __restrict__ inorm, int64_t n_tiles, float* __restrict__ tmax) {
+// per 256-item tile: max of v[0..n) (values beyond n count as 0)
+__global__ void __launch_bounds__(256) tc_tile_norm_kernel(const float* __restrict__ inorm, int64_t n_tiles, float* __restrict__ tmax,
+                                                           int64_t n) {
     const int lane = threadIdx.x & 31;
     const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (t >= n_tiles) return;
     float m = 0.f;
-    for (int c = lane; c < tc::TN; c += 32) m = fmaxf(m, inorm[t * tc::TN + c]);
+    for (int c = lane; c < tc::TN; c += 32) { const int64_t j = t * tc::TN + c; if (j < n) m = fmaxf(m, inorm[j]); }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
     if (lane == 0) tmax[t] = m;
@@ -173,6 +188,7 @@ struct SweepArgs {
     const float* unorm;        // [M_pad]
     const float* tile_inorm;   // [n_tiles]
     const float* col;          // mode 1: pop [N]; mode 0: col_bias [N] or nullptr
+    const float* tile_colmax;  // mode 1: max of pop over each 256-item tile
     // pass A
     float* cmax; int n_c;      // [M_pad][n_c] chunk maxima, row-major
     // pass B
@@ -192,20 +208,21 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
     // 1024 B alignment for the 128B-swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int kblocks = a.d / KB;
-    const uint32_t a_bytes = (uint32_t)TM * 128u * kblocks;      // A tile: kblocks sub-tiles of [128 rows x 128 B]
+    const uint32_t a1_bytes = (uint32_t)TM * 128u * kblocks;     // one A tile: kblocks sub-tiles of [128 rows x 128 B]
+    const uint32_t a_bytes = a1_bytes * MR;                      // MR user tiles stay resident for the whole sweep
     const uint32_t b_bytes = (uint32_t)TN * 128u * kblocks;      // B stage: kblocks sub-tiles of [256 rows x 128 B]
     unsigned char* sA = smem;
     unsigned char* sB = smem + a_bytes;
     unsigned char* tail = sB + (size_t)n_stages * b_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // full[8] empty[8] tfull[2] tempty[2] afull[1]
-    float* scol = reinterpret_cast<float*>(tail + 256);          // [2][256] column values (pop / bias) per accumulator stage
+    float* scol = reinterpret_cast<float*>(tail + 256);          // [2][256] column values (pop / bias), double-buffered by tile
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256 + 2048);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_tfull = smem_u32(bars + 16),
                    bar_tempty = smem_u32(bars + 18), bar_afull = smem_u32(bars + 20);
 
-    const int m_tile = blockIdx.x;
+    const int m_blk = blockIdx.x;                                // MR consecutive 128-row user tiles
     const int t_begin = blockIdx.y * a.tiles_per_split;
     const int t_end = min(a.n_tiles, t_begin + a.tiles_per_split);
     // tiles this CTA visits: pass A -> multiples of se; pass B -> all
@@ -225,12 +242,17 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Every B tile is multiplied with the MR resident user tiles in turn: sub-step sub = i * MR + mr uses accumulator
+    // stage sub & 1, so the epilogue of one user tile overlaps the MMAs of the next, and each B tile fetched from L2
+    // serves MR * 128 users.
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0 && n_my > 0) {
             mbar_expect_tx(bar_afull, a_bytes);
-            for (int kb = 0; kb < kblocks; ++kb)
-                tma_load_2d(smem_u32(sA + (size_t)kb * TM * 128), &tmA, bar_afull, kb * KB, m_tile * TM);
+            for (int mr = 0; mr < MR; ++mr)
+                for (int kb = 0; kb < kblocks; ++kb)
+                    tma_load_2d(smem_u32(sA + (size_t)mr * a1_bytes + (size_t)kb * TM * 128), &tmA, bar_afull, kb * KB,
+                                (m_blk * MR + mr) * TM);
             for (int i = 0; i < n_my; ++i) {
                 const int s = i % n_stages, ph = (i / n_stages) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
@@ -246,160 +268,203 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             mbar_wait(bar_afull, 0);
             for (int i = 0; i < n_my; ++i) {
                 const int s = i % n_stages, ph = (i / n_stages) & 1;
-                const int acc = i & 1, aph = (i >> 1) & 1;
-                mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
                 mbar_wait(bar_full + 8 * s, ph);
-                fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * TN;
-                for (int kb = 0; kb < kblocks; ++kb) {
-                    const uint64_t ad = make_desc(smem_u32(sA + (size_t)kb * TM * 128));
-                    const uint64_t bd = make_desc(smem_u32(sB + (size_t)s * b_bytes + (size_t)kb * TN * 128));
+                for (int mr = 0; mr < MR; ++mr) {
+                    const int sub = i * MR + mr, acc = sub & 1, aph = (sub >> 1) & 1;
+                    mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
+                    fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * TN;
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        const uint64_t ad = make_desc(smem_u32(sA + (size_t)mr * a1_bytes + (size_t)kb * TM * 128));
+                        const uint64_t bd = make_desc(smem_u32(sB + (size_t)s * b_bytes + (size_t)kb * TN * 128));
 #pragma unroll
-                    for (int k = 0; k < KB / 16; ++k)    // UMMA K = 16 bf16 = 32 B inside the 128 B swizzle row
-                        umma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
+                        for (int k = 0; k < KB / 16; ++k)    // UMMA K = 16 bf16 = 32 B inside the 128 B swizzle row
+                            umma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
+                    }
+                    if (mr == MR - 1) umma_commit(bar_empty + 8 * s);   // B stage may be refilled once these MMAs retire
+                    umma_commit(bar_tfull + 8 * acc);                   // accumulator ready for the epilogue
                 }
-                umma_commit(bar_empty + 8 * s);       // B stage may be refilled once these MMAs retire
-                umma_commit(bar_tfull + 8 * acc);     // accumulator ready for the epilogue
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread = (row 32q + lane, column group h of EPI_COLS columns) =====
+        // ===== epilogue: thread = (row 32q + lane of each resident user tile, column group h of EPI_COLS columns) =====
         const int q = warp & 3, h = (warp - 4) >> 2;
         const int e = (warp - 4) * 32 + lane;                    // epilogue thread index; the first 256 stage scol
-        const int64_t row = (int64_t)m_tile * TM + 32 * q + lane;
-        const bool row_ok = row < a.M;
-        const float un = a.unorm[row] * a.c_err;
         const bool use_col = MODE == 1 || a.col != nullptr;
-        float tau = 0.f;
-        if (PASS == 1) tau = row_ok ? a.tau[row] : INFINITY;
-        // pass B: this thread owns segment (split, h) of its row's candidate list -> no atomics
+        // pass B: this thread owns segment (split, h) of each of its rows' candidate lists -> no atomics
         const int seg = blockIdx.y * EPI_G + h;
-        int32_t* my_cand = PASS == 1 ? a.cand + ((int64_t)row * a.n_seg + seg) * a.seg_cap : nullptr;
-        int n_local = 0;
+        int64_t row[MR];
+        float un[MR], tau[MR];
+        int32_t* my_cand[MR];
+        int n_local[MR];
+#pragma unroll
+        for (int mr = 0; mr < MR; ++mr) {
+            row[mr] = ((int64_t)m_blk * MR + mr) * TM + 32 * q + lane;
+            un[mr] = a.unorm[row[mr]] * a.c_err;
+            tau[mr] = 0.f;
+            if (PASS == 1) tau[mr] = row[mr] < a.M ? a.tau[row[mr]] : INFINITY;
+            my_cand[mr] = PASS == 1 ? a.cand + (row[mr] * a.n_seg + seg) * a.seg_cap : nullptr;
+            n_local[mr] = 0;
+        }
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * EPI_COLS);
         for (int i = 0; i < n_my; ++i) {
             const int t = t_first + i * step;
-            const int acc = i & 1, aph = (i >> 1) & 1;
             const int64_t j0 = (int64_t)t * TN;
-            const float* sc = scol + acc * 256 + h * EPI_COLS;
+            const float* sc = scol + (i & 1) * 256 + h * EPI_COLS;
+            float pmax_t = INFINITY;
             if (use_col) {
                 if (e < TN) {
                     const int64_t j = j0 + e;
-                    scol[acc * 256 + e] = j < a.N ? __ldg(a.col + j) : 0.f;
+                    scol[(i & 1) * 256 + e] = j < a.N ? __ldg(a.col + j) : 0.f;
                 }
                 asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_G) : "memory");
+                if (MODE == 1 && PASS == 1) pmax_t = __ldg(a.tile_colmax + t);
             }
-            const float er = un * __ldg(a.tile_inorm + t);       // |s - s_lp| <= er for every item of this tile
-            mbar_wait(bar_tfull + 8 * acc, aph);
-            fence_after();
-            uint32_t va[32], vb[32];
-            float bests[EPI_CH];
-            const uint32_t tbase = lane_base + (uint32_t)(acc * TN);
-            tmem_ld32(tbase, va);
+            const float tn = __ldg(a.tile_inorm + t);
 #pragma unroll
-            for (int cc = 0; cc < EPI_CH; ++cc) {
-                uint32_t* v = (cc & 1) ? vb : va;
-                tmem_ld_wait();
-                if (cc < EPI_CH - 1) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), (cc & 1) ? va : vb);   // next chunk in flight
-                else {
-                    // all chunks are in registers: hand the accumulator stage back to the MMA warp
-                    fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
-                }
-                const int cb = cc * 32;                          // first column of this chunk inside this thread's half
-                const int64_t jb = j0 + h * EPI_COLS + cb;
-                if (PASS == 0) {
-                    float best = -INFINITY;
-                    if (jb + 32 <= a.N) {
-                        if (MODE == 1) {
-                            // lower bound of (elu(s)+1)*pop: f(x) >= x + 1 (also when x + 1 < 0: the product then is <= 0 <= y)
-                            const float k1 = 1.0f - er;
+            for (int mr = 0; mr < MR; ++mr) {
+                const int sub = i * MR + mr, acc = sub & 1, aph = (sub >> 1) & 1;
+                const float er = un[mr] * tn;                     // |s - s_lp| <= er for every item of this tile
+                mbar_wait(bar_tfull + 8 * acc, aph);
+                fence_after();
+                uint32_t va[32], vb[32];
+                float bests[EPI_CH];
+                const uint32_t tbase = lane_base + (uint32_t)(acc * TN);
+                tmem_ld32(tbase, va);
 #pragma unroll
-                            for (int c = 0; c < 32; c += 4) {
-                                const float4 p4 = *reinterpret_cast<const float4*>(sc + cb + c);
-                                best = fmaxf(best, (__uint_as_float(v[c + 0]) + k1) * p4.x);
-                                best = fmaxf(best, (__uint_as_float(v[c + 1]) + k1) * p4.y);
-                                best = fmaxf(best, (__uint_as_float(v[c + 2]) + k1) * p4.z);
-                                best = fmaxf(best, (__uint_as_float(v[c + 3]) + k1) * p4.w);
-                            }
-                        } else if (use_col) {
-                            const float k1 = -er;
+                for (int cc = 0; cc < EPI_CH; ++cc) {
+                    uint32_t* v = (cc & 1) ? vb : va;
+                    tmem_ld_wait();
+                    if (cc < EPI_CH - 1) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), (cc & 1) ? va : vb);   // next chunk in flight
+                    else {
+                        // all chunks are in registers: hand the accumulator stage back to the MMA warp
+                        fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                    }
+                    const int cb = cc * 32;                          // first column of this chunk inside this thread's group
+                    const int64_t jb = j0 + h * EPI_COLS + cb;
+                    if (PASS == 0) {
+                        float best = -INFINITY;
+                        if (jb + 32 <= a.N) {
+                            if (MODE == 1) {
+                                // lower bound of (elu(s)+1)*pop: f(x) >= x + 1 (also when x + 1 < 0: the product then is <= 0 <= y)
+                                const float k1 = 1.0f - er;
 #pragma unroll
-                            for (int c = 0; c < 32; c += 4) {
-                                const float4 p4 = *reinterpret_cast<const float4*>(sc + cb + c);
-                                best = fmaxf(best, (__uint_as_float(v[c + 0]) + k1) + p4.x);
-                                best = fmaxf(best, (__uint_as_float(v[c + 1]) + k1) + p4.y);
-                                best = fmaxf(best, (__uint_as_float(v[c + 2]) + k1) + p4.z);
-                                best = fmaxf(best, (__uint_as_float(v[c + 3]) + k1) + p4.w);
+                                for (int c = 0; c < 32; c += 4) {
+                                    const float4 p4 = lds_f4(smem_u32(sc + cb + c));
+                                    best = fmaxf(best, (__uint_as_float(v[c + 0]) + k1) * p4.x);
+                                    best = fmaxf(best, (__uint_as_float(v[c + 1]) + k1) * p4.y);
+                                    best = fmaxf(best, (__uint_as_float(v[c + 2]) + k1) * p4.z);
+                                    best = fmaxf(best, (__uint_as_float(v[c + 3]) + k1) * p4.w);
+                                }
+                            } else if (use_col) {
+                                const float k1 = -er;
+#pragma unroll
+                                for (int c = 0; c < 32; c += 4) {
+                                    const float4 p4 = lds_f4(smem_u32(sc + cb + c));
+                                    best = fmaxf(best, (__uint_as_float(v[c + 0]) + k1) + p4.x);
+                                    best = fmaxf(best, (__uint_as_float(v[c + 1]) + k1) + p4.y);
+                                    best = fmaxf(best, (__uint_as_float(v[c + 2]) + k1) + p4.z);
+                                    best = fmaxf(best, (__uint_as_float(v[c + 3]) + k1) + p4.w);
+                                }
+                            } else {
+                                // max first, bound after: s - er is monotone in s
+#pragma unroll
+                                for (int c = 0; c < 32; ++c) best = fmaxf(best, __uint_as_float(v[c]));
+                                best -= er;
                             }
                         } else {
-                            // max first, bound after: s - er is monotone in s
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) best = fmaxf(best, __uint_as_float(v[c]));
-                            best -= er;
-                        }
-                    } else {
-                        // the last tile: padded columns (zero rows) must not produce a bound
-                        for (int c = 0; c < 32; ++c) {
-                            if (jb + c >= a.N) break;
-                            const float s = __uint_as_float(v[c]);
-                            float y;
-                            if (MODE == 1) y = (s + (1.0f - er)) * sc[cb + c];
-                            else y = use_col ? (s - er) + sc[cb + c] : s - er;
-                            best = fmaxf(best, y);
-                        }
-                    }
-                    bests[cc] = best;
-                } else {
-                    uint32_t hits = 0;
-                    if (MODE == 1) {
-                        // upper bound: f(x) <= max(x + 1, 1)
-                        const float k1 = 1.0f + er;
-#pragma unroll
-                        for (int c = 0; c < 32; c += 4) {
-                            const float4 p4 = *reinterpret_cast<const float4*>(sc + cb + c);
-                            const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-                            for (int z = 0; z < 4; ++z) {
-                                const float y = fmaxf(__uint_as_float(v[c + z]) + k1, 1.0f) * pc[z];
-                                if (y >= tau) hits |= 1u << (c + z);
+                            // the last tile: padded columns (zero rows) must not produce a bound
+                            for (int c = 0; c < 32; ++c) {
+                                if (jb + c >= a.N) break;
+                                const float s = __uint_as_float(v[c]);
+                                float y;
+                                if (MODE == 1) y = (s + (1.0f - er)) * sc[cb + c];
+                                else y = use_col ? (s - er) + sc[cb + c] : s - er;
+                                best = fmaxf(best, y);
                             }
                         }
-                    } else if (use_col) {
-#pragma unroll
-                        for (int c = 0; c < 32; c += 4) {
-                            const float4 p4 = *reinterpret_cast<const float4*>(sc + cb + c);
-                            const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-                            for (int z = 0; z < 4; ++z)
-                                if ((__uint_as_float(v[c + z]) + er) + pc[z] >= tau) hits |= 1u << (c + z);
-                        }
+                        bests[cc] = best;
                     } else {
-                        const float thr = tau - er - fabsf(tau) * 4e-6f;      // s + er >= tau, rounding-safe
+                        // hit mask, accumulated as two exact fp32 sums of distinct powers of two (columns 0-15, 16-31)
+                        float hlo = 0.f, hhi = 0.f;
+                        const uint32_t sc_s = smem_u32(sc + cb);
+                        if (MODE == 1) {
+                            // upper bound: f(x) <= max(x + 1, 1), and max(a, 1) * p = max(a * p, p) for p >= 0.  When tau
+                            // exceeds every pop of the tile (the usual case: pop <= 1 < tau) only a * p >= tau can fire.
+                            const float k1 = 1.0f + er;
+                            const bool simple = __all_sync(0xffffffffu, tau[mr] > pmax_t);
+                            if (simple) {
 #pragma unroll
-                        for (int c = 0; c < 32; ++c)
-                            if (__uint_as_float(v[c]) >= thr) hits |= 1u << c;
-                    }
-                    while (hits) {
-                        const int c = __ffs(hits) - 1;
-                        hits &= hits - 1;
-                        const int64_t j = jb + c;
-                        if (j < a.N) {
-                            if (n_local < a.seg_cap) my_cand[n_local] = (int32_t)j;
-                            ++n_local;                               // > seg_cap marks the overflow
+                                for (int c = 0; c < 32; c += 4) {
+                                    const float4 p4 = lds_f4(sc_s + 4 * c);
+                                    const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                                    for (int z = 0; z < 4; ++z) {
+                                        const float f = fset_ge((__uint_as_float(v[c + z]) + k1) * pc[z], tau[mr]);
+                                        if (c + z < 16) hlo = fmaf(f, (float)(1u << ((c + z) & 15)), hlo);
+                                        else hhi = fmaf(f, (float)(1u << ((c + z) & 15)), hhi);
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < 32; c += 4) {
+                                    const float4 p4 = lds_f4(sc_s + 4 * c);
+                                    const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                                    for (int z = 0; z < 4; ++z) {
+                                        const float f = fset_ge(fmaxf(__uint_as_float(v[c + z]) + k1, 1.0f) * pc[z], tau[mr]);
+                                        if (c + z < 16) hlo = fmaf(f, (float)(1u << ((c + z) & 15)), hlo);
+                                        else hhi = fmaf(f, (float)(1u << ((c + z) & 15)), hhi);
+                                    }
+                                }
+                            }
+                        } else if (use_col) {
+#pragma unroll
+                            for (int c = 0; c < 32; c += 4) {
+                                const float4 p4 = lds_f4(sc_s + 4 * c);
+                                const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
+#pragma unroll
+                                for (int z = 0; z < 4; ++z) {
+                                    const float f = fset_ge((__uint_as_float(v[c + z]) + er) + pc[z], tau[mr]);
+                                    if (c + z < 16) hlo = fmaf(f, (float)(1u << ((c + z) & 15)), hlo);
+                                    else hhi = fmaf(f, (float)(1u << ((c + z) & 15)), hhi);
+                                }
+                            }
+                        } else {
+                            const float thr = tau[mr] - er - fabsf(tau[mr]) * 4e-6f;      // s + er >= tau, rounding-safe
+#pragma unroll
+                            for (int c = 0; c < 32; ++c) {
+                                const float f = fset_ge(__uint_as_float(v[c]), thr);
+                                if (c < 16) hlo = fmaf(f, (float)(1u << (c & 15)), hlo);
+                                else hhi = fmaf(f, (float)(1u << (c & 15)), hhi);
+                            }
+                        }
+                        uint32_t hits = (uint32_t)hlo | ((uint32_t)hhi << 16);
+                        while (hits) {
+                            const int c = __ffs(hits) - 1;
+                            hits &= hits - 1;
+                            const int64_t j = jb + c;
+                            if (j < a.N) {
+                                if (n_local[mr] < a.seg_cap) my_cand[mr][n_local[mr]] = (int32_t)j;
+                                ++n_local[mr];                           // > seg_cap marks the overflow
+                            }
                         }
                     }
                 }
-            }
-            if (PASS == 0) {   // this thread's chunk maxima of the tile: one vector store, row-major [row][n_c]
-                float* dst = a.cmax + (int64_t)row * a.n_c + (t / a.se) * 8 + h * EPI_CH;
-                if (EPI_CH == 4) *reinterpret_cast<float4*>(dst) = make_float4(bests[0], bests[1], bests[EPI_CH - 2], bests[EPI_CH - 1]);
-                else if (EPI_CH == 2) *reinterpret_cast<float2*>(dst) = make_float2(bests[0], bests[1]);
-                else dst[0] = bests[0];
+                if (PASS == 0) {   // this thread's chunk maxima of the tile: one vector store, row-major [row][n_c]
+                    float* dst = a.cmax + row[mr] * a.n_c + (t / a.se) * 8 + h * EPI_CH;
+                    if (EPI_CH == 4) *reinterpret_cast<float4*>(dst) = make_float4(bests[0], bests[1], bests[EPI_CH - 2], bests[EPI_CH - 1]);
+                    else if (EPI_CH == 2) *reinterpret_cast<float2*>(dst) = make_float2(bests[0], bests[1]);
+                    else dst[0] = bests[0];
+                }
             }
         }
-        if (PASS == 1) a.cnt[(int64_t)row * a.n_seg + seg] = n_local;
+        if (PASS == 1) {
+#pragma unroll
+            for (int mr = 0; mr < MR; ++mr) a.cnt[row[mr] * a.n_seg + seg] = n_local[mr];
+        }
     }
     fence_before();
     __syncthreads();
@@ -732,7 +797,7 @@ bool tc_supported(const EvalArgs& a) {
 
 size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     using namespace tc;
-    p->M_pad = (a.M + TM - 1) / TM * TM;
+    p->M_pad = (a.M + TM * MR - 1) / (TM * MR) * (TM * MR);
     p->N_pad = (a.N + TN - 1) / TN * TN;
     p->n_tiles = (int)(p->N_pad / TN);
     const int64_t n_chunks = (int64_t)p->n_tiles * 8;
@@ -742,7 +807,7 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     while ((n_chunks + se - 1) / se > TAU_MAX_KEYS) ++se;
     p->se = se;
     p->n_c = (p->n_tiles + se - 1) / se * 8;
-    const int m_tiles = (int)(p->M_pad / TM);
+    const int m_tiles = (int)(p->M_pad / (TM * MR));
     int splits = (148 * 2 + m_tiles - 1) / m_tiles;
     if (splits < 1) splits = 1;
     if (splits > p->n_tiles) splits = p->n_tiles;
@@ -762,6 +827,7 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->o_inorm = o; o += al256((size_t)p->N_pad * 4);
     p->o_unorm = o; o += al256((size_t)p->M_pad * 4);
     p->o_tnorm = o; o += al256((size_t)p->n_tiles * 4);
+    p->o_tcolmax = o; o += al256((size_t)p->n_tiles * 4);
     p->o_cmax = o; o += al256((size_t)p->n_c * p->M_pad * 4);
     p->o_tau = o; o += al256((size_t)p->M_pad * 4);
     p->o_cnt = o; o += al256((size_t)p->M_pad * p->n_seg * 4);
@@ -778,8 +844,8 @@ static int launch_sweep(const CUtensorMap& tmA, const CUtensorMap& tmB, const Sw
                         cudaStream_t st) {
     using namespace tc;
     const int kblocks = s.d / KB;
-    const size_t a_bytes = (size_t)TM * 128 * kblocks, b_bytes = (size_t)TN * 128 * kblocks;
-    int n_stages = (int)((200 * 1024 - a_bytes) / b_bytes);
+    const size_t a_bytes = (size_t)TM * 128 * kblocks * MR, b_bytes = (size_t)TN * 128 * kblocks;
+    int n_stages = (int)((204 * 1024 - a_bytes) / b_bytes);
     if (n_stages > 4) n_stages = 4;
     if (n_stages < 1) return 1;
     const size_t smem = 1024 + a_bytes + (size_t)n_stages * b_bytes + 256 + 2048 + 64;
@@ -803,12 +869,15 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, cudaS
     int32_t* cnt = (int32_t*)(b + p.o_cnt); int32_t* cand = (int32_t*)(b + p.o_cand);
     int32_t* flag = (int32_t*)(b + p.o_flag); int32_t* frows = (int32_t*)(b + p.o_frows);
     int32_t* fusers = (int32_t*)(b + p.o_fusers); int32_t* nflag = (int32_t*)(b + p.o_nflag);
-    const int m_tiles = (int)(p.M_pad / TM);
+    const int m_tiles = (int)(p.M_pad / (TM * MR));
 
     // prep
     tc_convert_rows_kernel<<<(unsigned)((p.N_pad * 32 + 255) / 256), 256, 0, st>>>(a.I, nullptr, a.N, p.N_pad, a.d, Ib, inorm);
     tc_convert_rows_kernel<<<(unsigned)((p.M_pad * 32 + 255) / 256), 256, 0, st>>>(a.U, a.users, a.M, p.M_pad, a.d, Ub, unorm);
-    tc_tile_norm_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(inorm, p.n_tiles, tnorm);
+    tc_tile_norm_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(inorm, p.n_tiles, tnorm, p.N_pad);
+    float* tcolmax = (float*)(b + p.o_tcolmax);
+    if (a.mode == 1)
+        tc_tile_norm_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(a.pop, p.n_tiles, tcolmax, a.N);
     cudaMemsetAsync(nflag, 0, 4, st);
 
     CUtensorMap tmA, tmB;
@@ -821,6 +890,7 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, cudaS
     s.c_err = 1.02f / 256.0f + (float)a.d / 2097152.0f;
     s.unorm = unorm; s.tile_inorm = tnorm;
     s.col = a.mode == 1 ? a.pop : a.col_bias;
+    s.tile_colmax = tcolmax;
     s.cmax = cmax; s.n_c = p.n_c; s.tau = tau; s.cand = cand; s.cnt = cnt; s.n_seg = p.n_seg; s.seg_cap = p.seg_cap;
 
     int rc = a.mode == 1 ? launch_sweep<1, 0>(tmA, tmB, s, p, m_tiles, st) : launch_sweep<0, 0>(tmA, tmB, s, p, m_tiles, st);
