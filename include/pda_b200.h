@@ -177,6 +177,10 @@ int pda_adam_apply(pda_model* m, void* stream);
 /* the same in two halves: part 1 = tables kept lazily (rank-local gradients; may run while the exchange of the other
  * gradient is in flight), part 2 = dense sweep of the remaining variables + loss / beta-power bookkeeping; 3 = both */
 int pda_adam_apply_part(pda_model* m, int part, void* stream);
+/* finer still, for callers that pipeline the exchange of a dense gradient with its consumption: the dense Adam sweep of
+ * rows [row_lo, row_hi) of one (densely kept) table; after the last range call pda_adam_apply_part(m, 8, stream) --
+ * loss / beta-power bookkeeping only */
+int pda_adam_dense_rows(pda_model* m, int which, int64_t row_lo, int64_t row_hi, void* stream);
 int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                          const float* pos_pop, const float* neg_pop, int64_t B, void* stream);
 /* loss3 of the last enqueued step (synchronises `stream`) */

@@ -63,6 +63,7 @@ PROTOTYPES = {
     "pda_forward_backward_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp]),
     "pda_adam_apply": (C.c_int, [c_vp, c_vp]),
     "pda_adam_apply_part": (C.c_int, [c_vp, C.c_int, c_vp]),
+    "pda_adam_dense_rows": (C.c_int, [c_vp, C.c_int, C.c_int64, C.c_int64, c_vp]),
     "pda_stage_batch_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp]),
     "pda_read_loss": (C.c_int, [c_vp, c_vp, c_vp]),
     "pda_read_loss_sums": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),

@@ -555,7 +555,8 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
 
 // TF1 Adam sweep over both tables (one kernel) + loss / beta-power bookkeeping
 // parts: 1 = the rank-local half (lazily maintained tables: their gradient never leaves the GPU),
-//        2 = the exchanged half (dense sweep of the remaining variables) + loss / beta-power bookkeeping, 3 = both.
+//        2 = the exchanged half (dense sweep of the remaining variables) + loss / beta-power bookkeeping, 3 = both,
+//        8 = bookkeeping only (the dense sweep was issued in row ranges through pda_adam_dense_rows).
 // Data-parallel callers run part 1 while the item-gradient all-reduce is in flight, then part 2.
 static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st, int parts = 3) {
     float* lr_slot = nullptr;
@@ -570,8 +571,8 @@ static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st, int part
             if (launch_adam_lazy_rows(la, 1, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
         }
     }
-    if (!(parts & 2)) return PDA_OK;
-    if (apply_adam) {
+    if (!(parts & (2 | 8))) return PDA_OK;
+    if (apply_adam && (parts & 2)) {
         AdamArgs a;
         memset(&a, 0, sizeof(a));
         bool any_dense = false;
@@ -582,8 +583,8 @@ static int enqueue_adam(pda_model* m, bool apply_adam, cudaStream_t st, int part
         }
         a.pw = m->pw; a.lr = m->cfg.lr;
         if (any_dense) { ProfScope ps(m, PDA_PROF_ADAM, st); launch_adam_dense(a, st); }
-        lr_slot = m->lr_hist + (m->step_no - m->lr_base);
     }
+    if (apply_adam) lr_slot = m->lr_hist + (m->step_no - m->lr_base);
     launch_finish_step(m->loss_acc, m->loss3, m->loss_sum, m->pw, m->last_B, m->cfg.regs, m->cfg.batch_size, apply_adam ? 1 : 0,
                        m->cfg.lr, lr_slot, st);
     if (apply_adam) {
@@ -637,8 +638,26 @@ int pda_forward_backward_device(pda_model* m, const int32_t* users, const int32_
     return PDA_OK;
 }
 
+int pda_adam_dense_rows(pda_model* m, int which, int64_t row_lo, int64_t row_hi, void* stream) {
+    if (!m || (which != PDA_TABLE_USER && which != PDA_TABLE_ITEM)) return fail(PDA_ERR_ARG, "bad argument");
+    const int t = which == PDA_TABLE_USER ? 0 : 1;
+    if (row_lo < 0 || row_hi > m->rows[t] || row_lo > row_hi) return fail(PDA_ERR_ARG, "row range outside the table");
+    if (m->adam_lazy[t]) return fail(PDA_ERR_STATE, "the table is kept lazily: there is no dense sweep to run on it");
+    if (row_lo == row_hi) return PDA_OK;
+    CK(cudaSetDevice(m->cfg.device));
+    AdamArgs a;
+    memset(&a, 0, sizeof(a));
+    const size_t off = (size_t)row_lo * m->d;
+    a.W[0] = m->W[t] + off; a.m[0] = m->Mo[t] + off; a.v[0] = m->Vo[t] + off; a.G[0] = m->G[t] + off;
+    a.n4[0] = (row_hi - row_lo) * m->d / 4;
+    a.pw = m->pw; a.lr = m->cfg.lr;
+    { ProfScope ps(m, PDA_PROF_ADAM, (cudaStream_t)stream); launch_adam_dense(a, (cudaStream_t)stream); }
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
 int pda_adam_apply_part(pda_model* m, int part, void* stream) {
-    if (!m || part < 1 || part > 3) return fail(PDA_ERR_ARG, "bad argument");
+    if (!m || (part != 1 && part != 2 && part != 3 && part != 8)) return fail(PDA_ERR_ARG, "bad argument");
     CK(cudaSetDevice(m->cfg.device));
     int rc = enqueue_adam(m, true, (cudaStream_t)stream, part);
     if (rc) return rc;

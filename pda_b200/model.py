@@ -244,6 +244,11 @@ class PDAModel:
         """part 1: lazily kept (rank-local) tables; part 2: dense sweep of the rest + bookkeeping; 3: both."""
         check(self.lib.pda_adam_apply_part(self._h, int(part), ptr(stream) if stream else None))
 
+    def adam_dense_rows(self, name, row_lo, row_hi, stream=0):
+        """dense Adam sweep of rows [row_lo, row_hi) of one densely kept table (pipelined gradient exchange)."""
+        check(self.lib.pda_adam_dense_rows(self._h, self._TABLES[name], int(row_lo), int(row_hi),
+                                           ptr(stream) if stream else None))
+
     def stage_batch(self, users, pos_items, neg_items, pos_pop=None, neg_pop=None, stream=0):
         u, p, n = _i32(users), _i32(pos_items), _i32(neg_items)
         pp = None if pos_pop is None else _f32(pos_pop)

@@ -29,12 +29,15 @@ def shard_range(n, world, rank):
 
 
 class ShardedTrainer:
-    def __init__(self, model, world=1, rank=0, reducer=None):
+    def __init__(self, model, world=1, rank=0, reducer=None, chunks=4):
         """reducer(tensor) -> None sums `tensor` in place over ranks (default: torch.distributed.all_reduce)."""
         self.model, self.world, self.rank = model, int(world), int(rank)
+        if int(world) > 1 and getattr(model, "train", "") == "temp_pop":
+            raise NotImplementedError("data-parallel training covers BPRMF / PD / PDG (the bias tables of BPR(t)-pop are not exchanged)")
         self._gi = self._acc = None
         self._reduce = reducer
         self._async_reduce = None
+        self.chunks = int(chunks)
         if self.world > 1:
             if hasattr(model, "set_adam_mode"):
                 # the item gradient is the sum over ranks: which item rows were touched is not known locally,
@@ -66,11 +69,19 @@ class ShardedTrainer:
             self._exchange()
             m.adam_apply(stream)
             return
-        works = [self._async_reduce(self._gi), self._async_reduce(self._acc)]
+        # the item gradient travels in row chunks: chunk k's all-reduce overlaps the dense Adam sweep of chunk k-1
+        # (and, first of all, the rank-local half of the optimizer)
+        n = m.n_items
+        nch = self.chunks if n >= 4096 * self.chunks else 1
+        bounds = [n * k // nch for k in range(nch + 1)]
+        works = [self._async_reduce(self._gi[bounds[k]:bounds[k + 1]]) for k in range(nch)]
+        wacc = self._async_reduce(self._acc)
         m.adam_apply(stream, part=1)
-        for w in works:
-            w.wait()               # stream-level dependency, the host does not block
-        m.adam_apply(stream, part=2)
+        for k in range(nch):
+            works[k].wait()        # stream-level dependency, the host does not block
+            m.adam_dense_rows("item_embedding", bounds[k], bounds[k + 1], stream)
+        wacc.wait()
+        m.adam_apply(stream, part=8)
 
     def train_sampled(self, seed, epoch, step0, n_steps, B, stream=0):
         m = self.model

@@ -104,3 +104,25 @@ def test_cli_runs_pd_on_douban(tmp_path):
     assert "training and testing end!!!!" in out
     ck = [f for _, _, fs in os.walk(tmp_path) for f in fs]
     assert "best_ckpt.ckpt.npz" in ck and "best_main_ckpt.ckpt.npz" in ck
+
+
+@needs_douban
+@pytest.mark.parametrize("train", ["normal", "condition", "temp_pop"])
+def test_cli_other_models_run_on_douban(tmp_path, train):
+    """BPRMF (+ the BPRMF-A gamma~ line search), PDG and BPR(t)-pop through the same CLI, 1 epoch each."""
+    cmd = [sys.executable, "-u", "MF/train_new_api.py", "--dataset", "douban", "--epoch", "1", "--save_flag", "0",
+           "--log_interval", "1", "--batch_size", "2048", "--lr", "1e-2", "--train", train, "--test", train, "--saveID", "t",
+           "--cuda", "0", "--regs", "1e-3", "--valid_set", "valid", "--pop_exp", "0.22", "--save_dir", str(tmp_path) + "/",
+           "--Ks", "[20,50]"]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    out = r.stdout
+    assert "training and testing end!!!!" in out and "batch_num: 3236" in out
+    rec = [float(a) for a, _ in re.findall(r"recall=\[([\d.]+), ([\d.]+)\]", out)]
+    assert len(rec) >= 3 and max(rec) > 0.01
+    if train == "normal":
+        assert "best expo:" in out and "BPRMF-A with injecting last stage pop(best gamma)" in out
+        expo = [float(x) for x in re.findall(r"expo: ([\d.]+) best expo", out)]
+        assert expo[0] == 0.04 and len(expo) >= 5            # 0.04, 0.06, ... until 5 non-improvements
+    if train == "temp_pop":
+        assert "running temproal pop MF" in out
