@@ -214,6 +214,12 @@ int pda_recommend_device(pda_model* m, const int32_t* users, int64_t M, int rec_
  * candidates rescored, max candidates of a row, rows whose candidate list overflowed, pass-A tile stride, sampled
  * chunks per row, item-range splits}.  Synchronises the device. */
 int pda_tc_last_stats(pda_model* m, int64_t* out);
+/* diagnostics: the raw tensor-core accumulators the filter compares -- out fp32 [M, n_items]:
+ * v[r][j] ~ (u_r . i_j + 1) * pop_j  (PDA_REC_WITH_POP),  u_r . i_j + col_bias_j,  or  u_r . i_j  (bf16 operands, fp32
+ * accumulation in TMEM); err_coef[2] = {cAB, cB} of the bound |v - exact| <= cAB |u| |c_j i_j| + cB |x_j|.
+ * Lets a test check operand layouts and the bound against fp64.  M <= 32768. */
+int pda_tc_debug_dense_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop,
+                            const float* col_bias, float* out, float* err_coef);
 /* dense scores -- replaces testing()/predict() (train_new_api.py:642-696): out fp32 [M, n_items], no mask */
 int pda_scores_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop, float* out);
 

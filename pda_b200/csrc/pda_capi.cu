@@ -956,6 +956,43 @@ int pda_tc_last_stats(pda_model* m, int64_t* out) {
     return PDA_OK;
 }
 
+int pda_tc_debug_dense_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop,
+                            const float* col_bias, float* out, float* err_coef) {
+    if (!m || !users || !out || M < 1 || M > 32768) return fail(PDA_ERR_ARG, "bad argument");
+    if (rec_type == PDA_REC_WITH_POP && !pop) return fail(PDA_ERR_ARG, "rec_type with_pop needs pop");
+    CK(cudaSetDevice(m->cfg.device));
+    EvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.U = m->W[0]; a.I = m->W[1]; a.N = m->nI; a.d = m->d; a.M = M; a.K = 1;
+    a.mode = rec_type == PDA_REC_WITH_POP ? 1 : 0;
+    if (!tc_supported(a)) return fail(PDA_ERR_ARG, "tensor-core eval needs embed_size in {64,128}, n_items >= 4096");
+    TcPlan plan;
+    const size_t need = tc_scratch_bytes(a, &plan);
+    CK(ensure_dev(&m->tc_buf, &m->tc_bytes, need));
+    const size_t nu = ((size_t)M * 4 + 255) / 256 * 256, nv = ((size_t)m->nI * 4 + 255) / 256 * 256;
+    const size_t nd = (size_t)M * plan.N_pad * 4;
+    CK(ensure_dev(&m->ev_buf, &m->ev_bytes, nu + 2 * nv + nd));
+    char* b = (char*)m->ev_buf;
+    int32_t* d_users = (int32_t*)b; float* d_pop = (float*)(b + nu); float* d_bias = (float*)(b + nu + nv);
+    float* d_dense = (float*)(b + nu + 2 * nv);
+    CK(cudaMemcpyAsync(d_users, users, (size_t)M * 4, cudaMemcpyHostToDevice, 0));
+    if (pop) CK(cudaMemcpyAsync(d_pop, pop, (size_t)m->nI * 4, cudaMemcpyHostToDevice, 0));
+    if (col_bias) CK(cudaMemcpyAsync(d_bias, col_bias, (size_t)m->nI * 4, cudaMemcpyHostToDevice, 0));
+    a.users = d_users; a.pop = pop ? d_pop : nullptr; a.col_bias = col_bias ? d_bias : nullptr;
+    flush_lazy(m, 0);
+    const int rc = launch_tc_debug_dense(a, m->tc_buf, plan, d_dense, 0);
+    if (rc) return fail(PDA_ERR_CUDA, "tensor-core sweep launch failed (stage %d): %s", rc, cudaGetErrorString(cudaGetLastError()));
+    CK(cudaMemcpy2DAsync(out, (size_t)m->nI * 4, d_dense, (size_t)plan.N_pad * 4, (size_t)m->nI * 4, (size_t)M,
+                         cudaMemcpyDeviceToHost, 0));
+    CK(cudaStreamSynchronize(0));
+    CK(cudaGetLastError());
+    if (err_coef) {
+        const float cA = 1.02f / 256.0f + (float)m->d / 2097152.0f, cB = (float)(m->d / 16 + 5) / 524288.0f;
+        err_coef[0] = cA + cB; err_coef[1] = cB;
+    }
+    return PDA_OK;
+}
+
 int pda_scores_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop, float* out) {
     if (!m || !users || !out || M < 1) return fail(PDA_ERR_ARG, "bad argument");
     if (rec_type == PDA_REC_WITH_POP && !pop) return fail(PDA_ERR_ARG, "rec_type with_pop needs pop");

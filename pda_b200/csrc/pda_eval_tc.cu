@@ -7,28 +7,44 @@
 // certificate; every id and score that leaves the library is computed by the exact fp32 spec
 // (sequential-k accumulate, spec_expf), identical to pda_eval_exact.cu and the oracle.
 //
-//   prep     I, U[users] -> bf16 copies (rows padded to the tile) + row norms; per-tile max item norm
-//   pass A   tcgen05 sweep over every `se`-th item tile: per (row, 32-column chunk) the maximum of a LOWER bound of
-//            the transformed score, with the column packed into the low mantissa bits        -> cmax[chunk][row]
-//   select   per row: drop chunk maxima that are train items (mask), tau = K-th largest of the rest.  K distinct
-//            unmasked items have exact score >= tau, so the exact K-th best is >= tau.
-//   pass B   tcgen05 sweep over ALL item tiles: items whose UPPER bound reaches tau -> cand[row][...]
+// The popularity adjust is folded INTO the GEMM, so the epilogue is one max / one compare per element:
+//   item operand   w_j = c_j * i_j          (c_j = pop_j for rec_type "condition", 1 otherwise), rounded to bf16
+//   extra K block  16 more bf16 columns: user side (1, 1, 1, 0...), item side (x_hi, x_mid, x_lo, 0...) with
+//                  x_j = pop_j ("condition") or the column bias (BPR(t)-pop) split into three bf16 pieces (24 bits)
+//   accumulator    v_j = sum_k bf(u_k) bf(w_jk) + x_j  ~  (s_j + 1) * pop_j   resp.   s_j + bias_j   resp.   s_j
+//
+//   prep     I, U[users] -> bf16 operands + row norms; per-tile max of |w_j| and |x_j|
+//   pass A   tcgen05 sweep over every `se`-th item tile: per (row, chunk of cw columns) max_j v_j - E, a LOWER bound
+//            of the best transformed score of the chunk                                          -> cmax[row][chunk]
+//   select   per row: drop chunks that hold a train item of the user (their maximum may be masked), tau = K-th
+//            largest of the rest.  K distinct unmasked items have exact score >= tau, so the exact K-th best is >= tau.
+//   pass B   tcgen05 sweep over ALL item tiles: items with v_j + E >= tau (UPPER bound reaches tau)  -> cand[row][...]
 //   rescore  per row: exact fp32 score of every candidate, transform, mask, sorted top-K.  The row is CERTIFIED when
 //            the candidate buffer did not overflow and at least K unmasked candidates have exact score >= tau
 //            (then every member of the exact top-K has upper bound >= its score >= K-th best >= tau, i.e. is a candidate).
 //   fallback rows that are not certified are recomputed by recommend_exact_kernel (count read on the device, no host sync).
 //
-// Bound: s = sum u_k i_k, s_lp = fp32-accumulated sum bf16(u_k) bf16(i_k):  |s - s_lp| <= c * |u| * |i|,
-// c = 1.02 * 2^-8 + d * 2^-21 (two RN roundings to 8 significant bits per product, accumulation slack, and the
-// distance between the sequential-k fp32 spec and the real-number dot).  f(x) = elu(x)+1 is increasing with
-// max(x+1, 0) <= f(x) <= max(x+1, 1), so no exp is needed in the sweeps.
+// Bound.  With acc_j the sequential-k fp32 dot of the spec and y_j the transformed score of the spec:
+//   |v_j - (acc_j [+1] ) c_j [- bias]| <= E_j = cA |u| |w_j| + cB (|u| |w_j| + |x_j|)
+//   cA = 1.02 * 2^-8 + d * 2^-21   two RN roundings to 8 significant bits per product; distance between the fp32
+//                                  sequential dot and the real dot
+//   cB = (d/16 + 5) * 2^-19        tensor-core accumulation (<= 2^-20 of the running magnitude per MMA instruction is
+//                                  assumed: 17 truncated addends), the bf16 x 3 split of x_j, the roundings of
+//                                  elu_p1 / spec_expf / the final product of the spec
+// f(x) = elu(x)+1 is increasing with max(x+1, 0) <= f(x) <= max(x+1, 1), pop >= 0, so for "condition"
+//   (acc+1) pop - E' <= y_j <= max((acc+1) pop, pop) + E'
+// The sweep tests the first branch of the upper bound only.  The "pop_j >= tau" branch is a property of the column
+// alone: the rescoring kernel adds those items itself (it scans the tiles whose largest pop reaches the row's tau --
+// none at all once tau > max pop, the fitted-model case).
 //
-// Sweep kernel: one CTA = 128 users (UMMA M) x a range of 256-item tiles (UMMA N).  Warp 0 lane 0 issues TMA
-// (128B-swizzled K-major tiles: A once, B through a ring), warp 1 lane 0 issues tcgen05.mma (kind::f16, bf16 -> fp32)
-// into two 256-column TMEM accumulator stages, warps 4-11 are the epilogue: tcgen05.ld 32x32b.x32 (a thread = one
-// user row x 32 items), bound, compare / max.  The score matrix never leaves TMEM.
+// Sweep kernel: one CTA = MR x 128 users resident in shared memory x a range of 128-item tiles.  Warp 0 lane 0
+// issues TMA (128B-swizzled K-major tiles + one 32B-swizzled 16-column tile; A once, B through a ring), warp 1 lane 0
+// issues tcgen05.mma (kind::f16, bf16 -> fp32) into a ring of four 128-column TMEM accumulators, warps 4-11 are the
+// epilogue: tcgen05.ld 32x32b.x32 (a thread = one user row x 64 items), FMNMX3 tree, compare.  The score matrix
+// never leaves TMEM.  Every B tile fetched from L2 serves MR * 128 users.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "pda_kernels.h"
 
@@ -36,13 +52,15 @@ namespace pda {
 
 namespace tc {
 
-constexpr int TM = 128, TN = 256, KB = 64;          // UMMA tile, K block (64 bf16 = one 128 B swizzle row)
-constexpr int MR = 2;                               // user tiles resident per CTA: every B tile from L2 serves MR * 128 users
-constexpr int EPI_G = 2;                            // epilogue warp groups: each owns TN / EPI_G columns of every tile (4 measured no faster)
-constexpr int EPI_COLS = TN / EPI_G;                // columns per thread and tile, in chunks of 32
-constexpr int EPI_CH = EPI_COLS / 32;
+constexpr int TM = 128, TN = 128, KB = 64;          // UMMA tile, K block (64 bf16 = one 128 B swizzle row)
+constexpr int KX = 16;                              // extra K block (one UMMA K step), 32 B rows, 32B swizzle
+constexpr int MR = 4;                               // user tiles resident per CTA: every B tile from L2 serves MR * 128 users
+constexpr int ACC = 4;                              // TMEM accumulator ring: ACC * TN = 512 columns
+constexpr int EPI_G = 2;                            // epilogue warp groups: each owns TN / EPI_G columns of every tile
+constexpr int EPI_COLS = TN / EPI_G;                // 64 columns per thread and tile = two tcgen05.ld x32
 constexpr int NT = 128 + 128 * EPI_G;               // warps: 0 TMA, 1 MMA, 2-3 idle, then 4 * EPI_G epilogue warps
-constexpr int CHUNK = 32;
+constexpr uint32_t A_KB_BYTES = TM * 128u, B_KB_BYTES = TN * 128u;      // one K block of an A / B tile
+constexpr uint32_t A_KX_BYTES = TM * 32u, B_KX_BYTES = TN * 32u;        // the extra block
 
 // ------------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -111,23 +129,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
-    float4 v;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
-    return v;
-}
-// 1.0f if a >= b else 0.0f (FSET): the compare result as a float, so the hit mask can be accumulated with FFMAs on
-// the FMA pipe instead of SEL / IADD3 on the half-rate ALU pipe
-__device__ __forceinline__ float fset_ge(float a, float b) {
-    float d;
-    asm("set.ge.f32.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-    return d;
-}
-
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1, layout type 2.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)2 << 61);
+}
+// K-major, 32B-swizzled operand tile (the 16-column extra block): rows of 32 B, 8-row groups 256 B apart, layout type 6.
+__device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
+           ((uint64_t)6 << 61);
 }
 // kind::f16: D = F32 (bit 4), A = B = BF16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
@@ -137,21 +147,28 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >
 // ------------------------------------------------------------------------------------------------------------
 // prep kernels
 // ------------------------------------------------------------------------------------------------------------
-// one warp per row: fp32 row -> bf16 row (+ L2 norm, rounded up); rows >= n_rows are zero padding.
+// one warp per row: fp32 row (times scale[r]) -> bf16 row + L2 norm of the scaled row (rounded up) + the row's 16-column
+// extra block: xone ? (1, 1, 1, 0...) : the three bf16 pieces of xcol[r].  Rows >= n_rows are zero padding.
 // src_rows == nullptr: row r of src; else row src_rows[r] (gather of the eval users).
 __global__ void __launch_bounds__(256) tc_convert_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ src_rows,
                                                               int64_t n_rows, int64_t n_pad, int d,
-                                                              __nv_bfloat16* __restrict__ dst, float* __restrict__ norm) {
+                                                              const float* __restrict__ scale, const float* __restrict__ xcol, int xone,
+                                                              __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dstx,
+                                                              float* __restrict__ norm, int32_t* __restrict__ neg_flag) {
     const int lane = threadIdx.x & 31;
     const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (r >= n_pad) return;
+    const bool real = r < n_rows;
     float sq = 0.f;
-    if (r < n_rows) {
+    if (real) {
+        const float sc = scale ? __ldg(scale + r) : 1.0f;
+        if (scale && lane == 0 && !(sc >= 0.0f)) atomicOr(neg_flag, 1);      // the bounds assume pop >= 0
         const float* s = src + (src_rows ? (int64_t)src_rows[r] : r) * d;
         for (int k = lane * 2; k < d; k += 64) {
             const float2 v = *reinterpret_cast<const float2*>(s + k);
-            sq = fmaf(v.x, v.x, fmaf(v.y, v.y, sq));
-            *reinterpret_cast<__nv_bfloat162*>(dst + r * d + k) = __floats2bfloat162_rn(v.x, v.y);
+            const float x = fmul(v.x, sc), y = fmul(v.y, sc);
+            sq = fmaf(x, x, fmaf(y, y, sq));
+            *reinterpret_cast<__nv_bfloat162*>(dst + r * d + k) = __floats2bfloat162_rn(x, y);
         }
     } else {
         for (int k = lane * 2; k < d; k += 64) *reinterpret_cast<__nv_bfloat162*>(dst + r * d + k) = __floats2bfloat162_rn(0.f, 0.f);
@@ -159,16 +176,31 @@ __global__ void __launch_bounds__(256) tc_convert_rows_kernel(const float* __res
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
     if (lane == 0) norm[r] = sqrtf(sq) * 1.00001f;
+    if (dstx && lane < 8) {
+        float e0 = 0.f, e1 = 0.f;
+        if (real && lane < 2) {
+            if (xone) { e0 = 1.0f; e1 = lane == 0 ? 1.0f : 0.0f; }
+            else if (xcol) {
+                const float x = __ldg(xcol + r);
+                const float hi = __bfloat162float(__float2bfloat16_rn(x));
+                const float r1 = fsub(x, hi);                                // exact
+                const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+                const float lo = __bfloat162float(__float2bfloat16_rn(fsub(r1, mid)));
+                if (lane == 0) { e0 = hi; e1 = mid; } else { e0 = lo; }
+            }
+        }
+        *reinterpret_cast<__nv_bfloat162*>(dstx + r * tc::KX + lane * 2) = __floats2bfloat162_rn(e0, e1);
+    }
 }
 
-// per 256-item tile: max of v[0..n) (values beyond n count as 0)
-__global__ void __launch_bounds__(256) tc_tile_norm_kernel(const float* __restrict__ inorm, int64_t n_tiles, float* __restrict__ tmax,
-                                                           int64_t n) {
+// per 128-item tile: max of |v[0..n)| (values beyond n count as 0)
+__global__ void __launch_bounds__(256) tc_tile_max_kernel(const float* __restrict__ v, int64_t n_tiles, float* __restrict__ tmax,
+                                                          int64_t n) {
     const int lane = threadIdx.x & 31;
     const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (t >= n_tiles) return;
     float m = 0.f;
-    for (int c = lane; c < tc::TN; c += 32) { const int64_t j = t * tc::TN + c; if (j < n) m = fmaxf(m, inorm[j]); }
+    for (int c = lane; c < tc::TN; c += 32) { const int64_t j = t * tc::TN + c; if (j < n) m = fmaxf(m, fabsf(v[j])); }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
     if (lane == 0) tmax[t] = m;
@@ -179,48 +211,102 @@ __global__ void __launch_bounds__(256) tc_tile_norm_kernel(const float* __restri
 // ------------------------------------------------------------------------------------------------------------
 struct SweepArgs {
     int64_t M, N;              // real rows / items
-    int64_t M_pad;             // rows of the bf16 user copy (multiple of 128)
-    int d;
-    int n_tiles;               // item tiles of 256
+    int64_t M_pad;             // rows of the bf16 user copy (multiple of MR * 128)
+    int d, kx;                 // kx = 1: the 16-column extra K block is present
+    int n_tiles;               // item tiles of 128
     int tiles_per_split;       // each CTA of blockIdx.y sweeps [y * tiles_per_split, ...)
     int se;                    // pass A: every se-th tile is sampled
-    float c_err;               // error-bound coefficient
+    float cAB, cB;             // E = cAB * |u| * max|w_j| + cB * max|x_j|  (maxima over the tile)
     const float* unorm;        // [M_pad]
-    const float* tile_inorm;   // [n_tiles]
-    const float* col;          // mode 1: pop [N]; mode 0: col_bias [N] or nullptr
-    const float* tile_colmax;  // mode 1: max of pop over each 256-item tile
+    const float* tile_inorm;   // [n_tiles] max |w_j|
+    const float* tile_col;     // [n_tiles] max |x_j| (nullptr when kx == 0)
     // pass A
-    float* cmax; int n_c;      // [M_pad][n_c] chunk maxima, row-major
+    float* cmax; int n_c, cw;  // [M_pad][n_c] chunk lower bounds, row-major; chunk width 32 or 64 columns
     // pass B
     const float* tau;          // [M_pad]
     int32_t* cand;             // [M_pad][n_seg][seg_cap] item ids, ascending inside a segment;
                                // segment = (item split, column half): exactly one owner thread, no atomics
     int32_t* cnt;              // [M_pad][n_seg] entries written (> seg_cap = overflow)
     int n_seg, seg_cap;
+    // pass 2 (diagnostics): the raw accumulators
+    float* dense; int64_t dense_ld;
 };
 
-template <int MODE, int PASS>
+namespace tc {
+
+__device__ __forceinline__ float max8(const uint32_t* v) {
+    float m = fmaxf(__uint_as_float(v[0]), __uint_as_float(v[1]));
+#pragma unroll
+    for (int c = 2; c < 8; ++c) m = fmaxf(m, __uint_as_float(v[c]));
+    return m;
+}
+
+// pass A: maximum of the chunk's 32 accumulators; columns >= N (zero padding rows of the item copy) do not count
+__device__ __forceinline__ float chunk_max(const uint32_t (&v)[32], bool tail, int64_t jb, int64_t N) {
+    if (!tail) return fmaxf(fmaxf(max8(v), max8(v + 8)), fmaxf(max8(v + 16), max8(v + 24)));
+    float m = -INFINITY;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) m = fmaxf(m, jb + c < N ? __uint_as_float(v[c]) : -INFINITY);
+    return m;
+}
+
+// the threshold the filter compares against: tau stepped down by more than the bound arithmetic can round up
+__device__ __forceinline__ float tau_lower(float t) { return t < INFINITY ? t - fabsf(t) * 2e-6f - 1e-30f : INFINITY; }
+
+// pass B: append the chunk's items with v >= thr to the thread's candidate segment.
+// Fast path = 18 FMNMX3/FMNMX + one compare for 32 elements; groups of 8 are scanned only when their maximum fires.
+__device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float thr, int64_t jb, int64_t N, int32_t* __restrict__ cand,
+                                           int& n, int cap) {
+    float sm[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) sm[g] = max8(v + 8 * g);
+    const float mx = fmaxf(fmaxf(sm[0], sm[1]), fmaxf(sm[2], sm[3]));
+    if (mx >= thr) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (sm[g] >= thr) {
+                uint32_t hits = 0;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) hits |= __uint_as_float(v[8 * g + c]) >= thr ? (1u << c) : 0u;
+                while (hits) {
+                    const int c = __ffs(hits) - 1;
+                    hits &= hits - 1;
+                    const int64_t j = jb + 8 * g + c;
+                    if (j < N) {
+                        if (n < cap) cand[n] = (int32_t)j;
+                        ++n;                                     // > cap marks the overflow
+                    }
+                }
+            }
+        }
+    }
+}
+
+}  // namespace tc
+
+template <int PASS>
 __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_constant__ CUtensorMap tmA,
-                                                              const __grid_constant__ CUtensorMap tmB, SweepArgs a,
+                                                              const __grid_constant__ CUtensorMap tmB,
+                                                              const __grid_constant__ CUtensorMap tmAx,
+                                                              const __grid_constant__ CUtensorMap tmBx, SweepArgs a,
                                                               int n_stages) {
     using namespace tc;
     extern __shared__ unsigned char smem_raw[];
     // 1024 B alignment for the 128B-swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int kblocks = a.d / KB;
-    const uint32_t a1_bytes = (uint32_t)TM * 128u * kblocks;     // one A tile: kblocks sub-tiles of [128 rows x 128 B]
-    const uint32_t a_bytes = a1_bytes * MR;                      // MR user tiles stay resident for the whole sweep
-    const uint32_t b_bytes = (uint32_t)TN * 128u * kblocks;      // B stage: kblocks sub-tiles of [256 rows x 128 B]
+    const uint32_t a1_bytes = A_KB_BYTES * kblocks + (a.kx ? A_KX_BYTES : 0u);     // one user tile: K blocks + extra block
+    const uint32_t a_bytes = a1_bytes * MR;                                        // MR user tiles stay resident for the whole sweep
+    const uint32_t b_bytes = B_KB_BYTES * kblocks + (a.kx ? B_KX_BYTES : 0u);      // one B stage
     unsigned char* sA = smem;
     unsigned char* sB = smem + a_bytes;
-    unsigned char* tail = sB + (size_t)n_stages * b_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(tail);          // full[8] empty[8] tfull[2] tempty[2] afull[1]
-    float* scol = reinterpret_cast<float*>(tail + 256);          // [2][256] column values (pop / bias), double-buffered by tile
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + 256 + 2048);
+    unsigned char* tail_p = sB + (size_t)n_stages * b_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(tail_p);        // full[8] empty[8] tfull[4] tempty[4] afull[1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail_p + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = smem_u32(bars), bar_empty = smem_u32(bars + 8), bar_tfull = smem_u32(bars + 16),
-                   bar_tempty = smem_u32(bars + 18), bar_afull = smem_u32(bars + 20);
+                   bar_tempty = smem_u32(bars + 20), bar_afull = smem_u32(bars + 24);
 
     const int m_blk = blockIdx.x;                                // MR consecutive 128-row user tiles
     const int t_begin = blockIdx.y * a.tiles_per_split;
@@ -232,34 +318,37 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4 * EPI_G); }
+        for (int s = 0; s < ACC; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4 * EPI_G); }
         mbar_init(bar_afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), 512);
+    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), ACC * TN);
     fence_before();
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     // Every B tile is multiplied with the MR resident user tiles in turn: sub-step sub = i * MR + mr uses accumulator
-    // stage sub & 1, so the epilogue of one user tile overlaps the MMAs of the next, and each B tile fetched from L2
-    // serves MR * 128 users.
+    // sub % ACC, so the epilogue of up to ACC - 1 earlier sub-steps overlaps the MMAs of the current one.
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0 && n_my > 0) {
             mbar_expect_tx(bar_afull, a_bytes);
-            for (int mr = 0; mr < MR; ++mr)
-                for (int kb = 0; kb < kblocks; ++kb)
-                    tma_load_2d(smem_u32(sA + (size_t)mr * a1_bytes + (size_t)kb * TM * 128), &tmA, bar_afull, kb * KB,
-                                (m_blk * MR + mr) * TM);
+            for (int mr = 0; mr < MR; ++mr) {
+                unsigned char* at = sA + (size_t)mr * a1_bytes;
+                const int r0 = (m_blk * MR + mr) * TM;
+                for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(smem_u32(at + (size_t)kb * A_KB_BYTES), &tmA, bar_afull, kb * KB, r0);
+                if (a.kx) tma_load_2d(smem_u32(at + (size_t)kblocks * A_KB_BYTES), &tmAx, bar_afull, 0, r0);
+            }
             for (int i = 0; i < n_my; ++i) {
                 const int s = i % n_stages, ph = (i / n_stages) & 1;
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 mbar_expect_tx(bar_full + 8 * s, b_bytes);
                 const int t = t_first + i * step;
+                unsigned char* bt = sB + (size_t)s * b_bytes;
                 for (int kb = 0; kb < kblocks; ++kb)
-                    tma_load_2d(smem_u32(sB + (size_t)s * b_bytes + (size_t)kb * TN * 128), &tmB, bar_full + 8 * s, kb * KB, t * TN);
+                    tma_load_2d(smem_u32(bt + (size_t)kb * B_KB_BYTES), &tmB, bar_full + 8 * s, kb * KB, t * TN);
+                if (a.kx) tma_load_2d(smem_u32(bt + (size_t)kblocks * B_KB_BYTES), &tmBx, bar_full + 8 * s, 0, t * TN);
             }
         }
     } else if (warp == 1) {
@@ -269,195 +358,87 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             for (int i = 0; i < n_my; ++i) {
                 const int s = i % n_stages, ph = (i / n_stages) & 1;
                 mbar_wait(bar_full + 8 * s, ph);
+                unsigned char* bt = sB + (size_t)s * b_bytes;
                 for (int mr = 0; mr < MR; ++mr) {
-                    const int sub = i * MR + mr, acc = sub & 1, aph = (sub >> 1) & 1;
+                    const int sub = i * MR + mr, acc = sub % ACC, aph = (sub / ACC) & 1;
                     mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
                     fence_after();
                     const uint32_t d_tmem = tmem_base + (uint32_t)acc * TN;
+                    unsigned char* at = sA + (size_t)mr * a1_bytes;
                     for (int kb = 0; kb < kblocks; ++kb) {
-                        const uint64_t ad = make_desc(smem_u32(sA + (size_t)mr * a1_bytes + (size_t)kb * TM * 128));
-                        const uint64_t bd = make_desc(smem_u32(sB + (size_t)s * b_bytes + (size_t)kb * TN * 128));
+                        const uint64_t ad = make_desc(smem_u32(at + (size_t)kb * A_KB_BYTES));
+                        const uint64_t bd = make_desc(smem_u32(bt + (size_t)kb * B_KB_BYTES));
 #pragma unroll
                         for (int k = 0; k < KB / 16; ++k)    // UMMA K = 16 bf16 = 32 B inside the 128 B swizzle row
                             umma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
                     }
+                    if (a.kx)                                // + x_j: (1, 1, 1, 0...) . (x_hi, x_mid, x_lo, 0...)
+                        umma_bf16(d_tmem, make_desc_sw32(smem_u32(at + (size_t)kblocks * A_KB_BYTES)),
+                                  make_desc_sw32(smem_u32(bt + (size_t)kblocks * B_KB_BYTES)), IDESC, 1u);
                     if (mr == MR - 1) umma_commit(bar_empty + 8 * s);   // B stage may be refilled once these MMAs retire
                     umma_commit(bar_tfull + 8 * acc);                   // accumulator ready for the epilogue
                 }
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: thread = (row 32q + lane of each resident user tile, column group h of EPI_COLS columns) =====
+        // ===== epilogue: thread = (row 32q + lane of each resident user tile, column half h of every tile) =====
         const int q = warp & 3, h = (warp - 4) >> 2;
-        const int e = (warp - 4) * 32 + lane;                    // epilogue thread index; the first 256 stage scol
-        const bool use_col = MODE == 1 || a.col != nullptr;
         // pass B: this thread owns segment (split, h) of each of its rows' candidate lists -> no atomics
         const int seg = blockIdx.y * EPI_G + h;
         int64_t row[MR];
-        float un[MR], tau[MR];
+        float unAB[MR], tl[MR];
         int32_t* my_cand[MR];
         int n_local[MR];
 #pragma unroll
         for (int mr = 0; mr < MR; ++mr) {
             row[mr] = ((int64_t)m_blk * MR + mr) * TM + 32 * q + lane;
-            un[mr] = a.unorm[row[mr]] * a.c_err;
-            tau[mr] = 0.f;
-            if (PASS == 1) tau[mr] = row[mr] < a.M ? a.tau[row[mr]] : INFINITY;
+            unAB[mr] = a.unorm[row[mr]] * a.cAB;
+            tl[mr] = INFINITY;
+            if (PASS == 1 && row[mr] < a.M) tl[mr] = tau_lower(a.tau[row[mr]]);
             my_cand[mr] = PASS == 1 ? a.cand + (row[mr] * a.n_seg + seg) * a.seg_cap : nullptr;
             n_local[mr] = 0;
         }
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * EPI_COLS);
         for (int i = 0; i < n_my; ++i) {
             const int t = t_first + i * step;
-            const int64_t j0 = (int64_t)t * TN;
-            const float* sc = scol + (i & 1) * 256 + h * EPI_COLS;
-            float pmax_t = INFINITY;
-            if (use_col) {
-                if (e < TN) {
-                    const int64_t j = j0 + e;
-                    scol[(i & 1) * 256 + e] = j < a.N ? __ldg(a.col + j) : 0.f;
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(128 * EPI_G) : "memory");
-                if (MODE == 1 && PASS == 1) pmax_t = __ldg(a.tile_colmax + t);
-            }
+            const int64_t j0 = (int64_t)t * TN + h * EPI_COLS;       // first column of this thread's half
             const float tn = __ldg(a.tile_inorm + t);
+            const float tcol = a.tile_col ? __ldg(a.tile_col + t) : 0.f;
+            const float eb = fmaf(a.cB, tcol, 1e-30f);
+            const bool tail = j0 + EPI_COLS > a.N;
 #pragma unroll
             for (int mr = 0; mr < MR; ++mr) {
-                const int sub = i * MR + mr, acc = sub & 1, aph = (sub >> 1) & 1;
-                const float er = un[mr] * tn;                     // |s - s_lp| <= er for every item of this tile
+                const int sub = i * MR + mr, acc = sub % ACC, aph = (sub / ACC) & 1;
+                float E = fmaf(unAB[mr], tn, eb);                    // |v_j - its real-number meaning| <= E on this tile
+                E = fmaf(E, 2e-6f, E);
                 mbar_wait(bar_tfull + 8 * acc, aph);
                 fence_after();
                 uint32_t va[32], vb[32];
-                float bests[EPI_CH];
                 const uint32_t tbase = lane_base + (uint32_t)(acc * TN);
                 tmem_ld32(tbase, va);
+                tmem_ld32(tbase + 32, vb);
+                tmem_ld_wait();
+                // both chunks are in registers: hand the accumulator back to the MMA warp
+                fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                if (PASS == 0) {
+                    float la = chunk_max(va, tail, j0, a.N) - E, lb = chunk_max(vb, tail, j0 + 32, a.N) - E;
+                    la = la > -INFINITY ? la - fabsf(la) * 2e-6f : la;
+                    lb = lb > -INFINITY ? lb - fabsf(lb) * 2e-6f : lb;
+                    float* dst = a.cmax + row[mr] * a.n_c;
+                    if (a.cw == 32) *reinterpret_cast<float2*>(dst + (t / a.se) * 4 + h * 2) = make_float2(la, lb);
+                    else dst[(t / a.se) * 2 + h] = fmaxf(la, lb);
+                } else if (PASS == 1) {
+                    const float thr = tl[mr] - E;                     // inf stays inf: no candidates for this row
+                    scan_chunk(va, thr, j0, a.N, my_cand[mr], n_local[mr], a.seg_cap);
+                    scan_chunk(vb, thr, j0 + 32, a.N, my_cand[mr], n_local[mr], a.seg_cap);
+                } else {
+                    if (row[mr] < a.M) {
+                        float* dst = a.dense + row[mr] * a.dense_ld + j0;
 #pragma unroll
-                for (int cc = 0; cc < EPI_CH; ++cc) {
-                    uint32_t* v = (cc & 1) ? vb : va;
-                    tmem_ld_wait();
-                    if (cc < EPI_CH - 1) tmem_ld32(tbase + (uint32_t)((cc + 1) * 32), (cc & 1) ? va : vb);   // next chunk in flight
-                    else {
-                        // all chunks are in registers: hand the accumulator stage back to the MMA warp
-                        fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+                        for (int c = 0; c < 32; ++c) { dst[c] = __uint_as_float(va[c]); dst[32 + c] = __uint_as_float(vb[c]); }
                     }
-                    const int cb = cc * 32;                          // first column of this chunk inside this thread's group
-                    const int64_t jb = j0 + h * EPI_COLS + cb;
-                    if (PASS == 0) {
-                        float best = -INFINITY;
-                        if (jb + 32 <= a.N) {
-                            if (MODE == 1) {
-                                // lower bound of (elu(s)+1)*pop: f(x) >= x + 1 (also when x + 1 < 0: the product then is <= 0 <= y)
-                                const float k1 = 1.0f - er;
-#pragma unroll
-                                for (int c = 0; c < 32; c += 4) {
-                                    const float4 p4 = lds_f4(smem_u32(sc + cb + c));
-                                    best = fmaxf(best, (__uint_as_float(v[c + 0]) + k1) * p4.x);
-                                    best = fmaxf(best, (__uint_as_float(v[c + 1]) + k1) * p4.y);
-                                    best = fmaxf(best, (__uint_as_float(v[c + 2]) + k1) * p4.z);
-                                    best = fmaxf(best, (__uint_as_float(v[c + 3]) + k1) * p4.w);
-                                }
-                            } else if (use_col) {
-                                const float k1 = -er;
-#pragma unroll
-                                for (int c = 0; c < 32; c += 4) {
-                                    const float4 p4 = lds_f4(smem_u32(sc + cb + c));
-                                    best = fmaxf(best, (__uint_as_float(v[c + 0]) + k1) + p4.x);
-                                    best = fmaxf(best, (__uint_as_float(v[c + 1]) + k1) + p4.y);
-                                    best = fmaxf(best, (__uint_as_float(v[c + 2]) + k1) + p4.z);
-                                    best = fmaxf(best, (__uint_as_float(v[c + 3]) + k1) + p4.w);
-                                }
-                            } else {
-                                // max first, bound after: s - er is monotone in s
-#pragma unroll
-                                for (int c = 0; c < 32; ++c) best = fmaxf(best, __uint_as_float(v[c]));
-                                best -= er;
-                            }
-                        } else {
-                            // the last tile: padded columns (zero rows) must not produce a bound
-                            for (int c = 0; c < 32; ++c) {
-                                if (jb + c >= a.N) break;
-                                const float s = __uint_as_float(v[c]);
-                                float y;
-                                if (MODE == 1) y = (s + (1.0f - er)) * sc[cb + c];
-                                else y = use_col ? (s - er) + sc[cb + c] : s - er;
-                                best = fmaxf(best, y);
-                            }
-                        }
-                        bests[cc] = best;
-                    } else {
-                        // hit mask, accumulated as two exact fp32 sums of distinct powers of two (columns 0-15, 16-31)
-                        float hlo = 0.f, hhi = 0.f;
-                        const uint32_t sc_s = smem_u32(sc + cb);
-                        if (MODE == 1) {
-                            // upper bound: f(x) <= max(x + 1, 1), and max(a, 1) * p = max(a * p, p) for p >= 0.  When tau
-                            // exceeds every pop of the tile (the usual case: pop <= 1 < tau) only a * p >= tau can fire.
-                            const float k1 = 1.0f + er;
-                            const bool simple = __all_sync(0xffffffffu, tau[mr] > pmax_t);
-                            if (simple) {
-#pragma unroll
-                                for (int c = 0; c < 32; c += 4) {
-                                    const float4 p4 = lds_f4(sc_s + 4 * c);
-                                    const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-                                    for (int z = 0; z < 4; ++z) {
-                                        const float f = fset_ge((__uint_as_float(v[c + z]) + k1) * pc[z], tau[mr]);
-                                        if (c + z < 16) hlo = fmaf(f, (float)(1u << ((c + z) & 15)), hlo);
-                                        else hhi = fmaf(f, (float)(1u << ((c + z) & 15)), hhi);
-                                    }
-                                }
-                            } else {
-#pragma unroll
-                                for (int c = 0; c < 32; c += 4) {
-                                    const float4 p4 = lds_f4(sc_s + 4 * c);
-                                    const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-                                    for (int z = 0; z < 4; ++z) {
-                                        const float f = fset_ge(fmaxf(__uint_as_float(v[c + z]) + k1, 1.0f) * pc[z], tau[mr]);
-                                        if (c + z < 16) hlo = fmaf(f, (float)(1u << ((c + z) & 15)), hlo);
-                                        else hhi = fmaf(f, (float)(1u << ((c + z) & 15)), hhi);
-                                    }
-                                }
-                            }
-                        } else if (use_col) {
-#pragma unroll
-                            for (int c = 0; c < 32; c += 4) {
-                                const float4 p4 = lds_f4(sc_s + 4 * c);
-                                const float pc[4] = {p4.x, p4.y, p4.z, p4.w};
-#pragma unroll
-                                for (int z = 0; z < 4; ++z) {
-                                    const float f = fset_ge((__uint_as_float(v[c + z]) + er) + pc[z], tau[mr]);
-                                    if (c + z < 16) hlo = fmaf(f, (float)(1u << ((c + z) & 15)), hlo);
-                                    else hhi = fmaf(f, (float)(1u << ((c + z) & 15)), hhi);
-                                }
-                            }
-                        } else {
-                            const float thr = tau[mr] - er - fabsf(tau[mr]) * 4e-6f;      // s + er >= tau, rounding-safe
-#pragma unroll
-                            for (int c = 0; c < 32; ++c) {
-                                const float f = fset_ge(__uint_as_float(v[c]), thr);
-                                if (c < 16) hlo = fmaf(f, (float)(1u << (c & 15)), hlo);
-                                else hhi = fmaf(f, (float)(1u << (c & 15)), hhi);
-                            }
-                        }
-                        uint32_t hits = (uint32_t)hlo | ((uint32_t)hhi << 16);
-                        while (hits) {
-                            const int c = __ffs(hits) - 1;
-                            hits &= hits - 1;
-                            const int64_t j = jb + c;
-                            if (j < a.N) {
-                                if (n_local[mr] < a.seg_cap) my_cand[mr][n_local[mr]] = (int32_t)j;
-                                ++n_local[mr];                           // > seg_cap marks the overflow
-                            }
-                        }
-                    }
-                }
-                if (PASS == 0) {   // this thread's chunk maxima of the tile: one vector store, row-major [row][n_c]
-                    float* dst = a.cmax + row[mr] * a.n_c + (t / a.se) * 8 + h * EPI_CH;
-                    if (EPI_CH == 4) *reinterpret_cast<float4*>(dst) = make_float4(bests[0], bests[1], bests[EPI_CH - 2], bests[EPI_CH - 1]);
-                    else if (EPI_CH == 2) *reinterpret_cast<float2*>(dst) = make_float2(bests[0], bests[1]);
-                    else dst[0] = bests[0];
                 }
             }
         }
@@ -468,11 +449,11 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
     }
     fence_before();
     __syncthreads();
-    if (warp == 1) { __syncwarp(); fence_after(); tmem_dealloc(tmem_base, 512); }
+    if (warp == 1) { __syncwarp(); fence_after(); tmem_dealloc(tmem_base, ACC * TN); }
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// tau selection: one warp per row; keys = chunk maxima with the column packed in the low 5 mantissa bits
+// tau selection: one warp per row; keys = the chunk lower bounds of pass A
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t f2key(float f) { uint32_t b = __float_as_uint(f); return (b & 0x80000000u) ? ~b : (b | 0x80000000u); }
 __device__ __forceinline__ float key2f(uint32_t k) { return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k); }
@@ -486,7 +467,7 @@ __device__ __forceinline__ bool csr_row_contains(const int32_t* __restrict__ ite
     return lo < end && __ldg(items + lo) == c;
 }
 
-constexpr int TAU_MAX_KEYS = 2048;
+constexpr int TAU_MAX_KEYS = 4096;
 
 // K-th largest of n 32-bit keys in shared memory (one warp): 4-pass MSB radix select, 256-bin histogram per pass.
 // Returns the key value; *n_greater = number of keys strictly greater.  hist: 256 ints of per-warp shared memory.
@@ -539,15 +520,15 @@ __device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t* keys, int n
 
 // one warp per row, n_c keys + 256 histogram bins per warp in dynamic shared memory
 __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restrict__ cmax, int n_c, int64_t M, int64_t M_pad,
-                                                            int se, const int32_t* __restrict__ users,
+                                                            int se, int cw, const int32_t* __restrict__ users,
                                                             const int64_t* __restrict__ mask_indptr,
                                                             const int32_t* __restrict__ mask_items, int K,
-                                                            float* __restrict__ tau) {
+                                                            const int32_t* __restrict__ neg_flag, float* __restrict__ tau) {
     extern __shared__ uint32_t tau_keys[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 4 + w;
     if (row >= M_pad) return;
-    if (row >= M) { if (lane == 0) tau[row] = INFINITY; return; }
+    if (row >= M || *neg_flag) { if (lane == 0) tau[row] = INFINITY; return; }    // negative pop: no filter, exact kernel
     uint32_t* kk = tau_keys + (size_t)w * (n_c + 256);
     int* hist = reinterpret_cast<int*>(kk + n_c);
     for (int c = lane; c < n_c; c += 32) {
@@ -556,7 +537,8 @@ __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restr
     }
     __syncwarp();
     // A sampled chunk that holds ANY train item of this user is dropped: its maximum may belong to a masked item.
-    // sampled chunk c = (sampled tile c/8, chunk c%8) covers items [(c/8)*se*256 + (c%8)*32, +32)
+    // chunk c = (sampled tile c / cpt, chunk c % cpt) covers items [(c / cpt) * se * TN + (c % cpt) * cw, + cw)
+    const int cpt = tc::TN / cw;
     if (mask_indptr) {
         const int u = users[row];
         const int64_t lo = mask_indptr[u], hi = mask_indptr[u + 1];
@@ -564,7 +546,7 @@ __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restr
             const int32_t it = __ldg(mask_items + z);
             const int tile = it / tc::TN;
             if (tile % se == 0) {
-                const int c = (tile / se) * 8 + ((it % tc::TN) >> 5);
+                const int c = (tile / se) * cpt + (it % tc::TN) / cw;
                 if (c < n_c) kk[c] = 0u;
             }
         }
@@ -580,10 +562,9 @@ __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restr
     }
     int above;
     const uint32_t kth = warp_kth_largest(kk, n_c, K, hist, lane, &above);
-    if (lane == 0) {
-        const float t = key2f(kth);
-        tau[row] = t - fabsf(t) * 1e-5f - 1e-30f;      // the bound arithmetic of the sweep rounds: step down
-    }
+    float t = key2f(kth);
+    t = t - fabsf(t) * 1e-5f - 1e-30f;
+    if (lane == 0) tau[row] = t;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -599,6 +580,7 @@ struct RescoreArgs {
     const float* tau;
     int K;
     int rc;             // per-row capacity of the compacted candidate list in shared memory
+    const float* tile_col; int n_tiles;     // mode 1: max pop of every 128-item tile (the pop branch of the upper bound)
     int32_t* ids_out; float* scores_out;
     int32_t* flag;      // [M] 1 = not certified
 };
@@ -656,9 +638,51 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
     }
     __syncwarp();
 
+    // 1b. "condition": f(s) * pop <= max((s + 1) * pop, pop), and the sweep only tests the first branch.  Items with
+    //     pop_j >= tau are candidates by the second one whatever the user: scan the tiles whose largest pop reaches tau
+    //     (none at all once tau > max pop, the fitted-model case), skip what the sweep already delivered.
+    int n_extra = 0;
+    if (a.mode == 1) {
+        const float tl = tc::tau_lower(a.tau[row]);
+        for (int tb = 0; tb < a.n_tiles && tot + n_extra <= RC; tb += 32) {
+            const int t = tb + lane;
+            unsigned bal = __ballot_sync(0xffffffffu, t < a.n_tiles && __ldg(a.tile_col + t) >= tl);
+            while (bal) {
+                const int th = tb + __ffs(bal) - 1;
+                bal &= bal - 1;
+#pragma unroll
+                for (int k = 0; k < tc::TN / 32; ++k) {
+                    const int cidx = k * 32 + lane;
+                    const int64_t j = (int64_t)th * tc::TN + cidx;
+                    bool c = j < a.N && __ldg(a.pop + j) >= tl;
+                    if (c) {
+                        const int sg = (th / a.tiles_per_split) * tc::EPI_G + cidx / tc::EPI_COLS;
+                        const int send = soff[sg + 1];
+                        int l = soff[sg], r = send;
+                        while (l < r) {
+                            const int mid = (l + r) >> 1;
+                            if (cid[mid] < (int)j) l = mid + 1; else r = mid;
+                        }
+                        c = !(l < send && cid[l] == (int)j);
+                    }
+                    const unsigned b2 = __ballot_sync(0xffffffffu, c);
+                    if (c) {
+                        const int pos = tot + n_extra + __popc(b2 & ((1u << lane) - 1u));
+                        if (pos < RC) cid[pos] = (int)j;
+                    }
+                    n_extra += __popc(b2);
+                }
+            }
+        }
+        if (tot + n_extra > RC) { if (lane == 0) a.flag[row] = 1; return; }
+        __syncwarp();
+    }
+
     // 2. masked items: id -> ~id (negative)
     if (a.mask_indptr) {
         const int64_t lo = a.mask_indptr[u], hi = a.mask_indptr[u + 1];
+        for (int c = tot + lane; c < tot + n_extra; c += 32)       // pop-branch extras live outside the segments
+            if (csr_row_contains(a.mask_items, lo, hi, cid[c])) cid[c] = ~cid[c];
         for (int64_t z = lo + lane; z < hi; z += 32) {
             const int32_t it = __ldg(a.mask_items + z);
             const int sg = (it / tc::TN / a.tiles_per_split) * tc::EPI_G + (it % tc::TN) / tc::EPI_COLS;
@@ -666,12 +690,15 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
             int l = soff[sg], r = send;
             while (l < r) {
                 const int mid = (l + r) >> 1;
-                if (cid[mid] < it) l = mid + 1; else r = mid;
+                const int cv = cid[mid];                     // another lane may have flipped it already: compare the id
+                if ((cv < 0 ? ~cv : cv) < it) l = mid + 1; else r = mid;
             }
             if (l < send && cid[l] == it) cid[l] = ~it;
         }
         __syncwarp();
     }
+
+    tot += n_extra;
 
     // 3. exact scores
     const float tau = a.tau[row];
@@ -775,17 +802,17 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// bf16 [rows, d] row-major, box = 64 columns (128 B) x box_rows, 128B swizzle
-static int make_map(CUtensorMap* m, const void* base, int64_t rows, int d, int box_rows) {
+// bf16 [rows, cols] row-major, box = box_cols columns x 128 rows; 64 columns (128 B) -> 128B swizzle, 16 (32 B) -> 32B swizzle
+static int make_map(CUtensorMap* m, const void* base, int64_t rows, int cols, int box_cols) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return 1;
-    cuuint64_t dims[2] = {(cuuint64_t)d, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)d * 2};
-    cuuint32_t box[2] = {(cuuint32_t)tc::KB, (cuuint32_t)box_rows};
+    cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)cols * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)tc::TM};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == tc::KB ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_32B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : 2;
 }
 
@@ -795,26 +822,50 @@ bool tc_supported(const EvalArgs& a) {
     return (a.d == 64 || a.d == 128) && a.N >= 4096 && a.K >= 1 && a.K <= 128 && a.N < (1LL << 31) - 512;
 }
 
+static int env_int(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e && *e ? atoi(e) : dflt;
+}
+
 size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     using namespace tc;
+    static_assert(TM == TN, "one tensor-map box shape serves both operands");
     p->M_pad = (a.M + TM * MR - 1) / (TM * MR) * (TM * MR);
     p->N_pad = (a.N + TN - 1) / TN * TN;
     p->n_tiles = (int)(p->N_pad / TN);
-    const int64_t n_chunks = (int64_t)p->n_tiles * 8;
-    // pass A samples every se-th tile; its cost ~ 1/se, the candidate count ~ se: keep as many chunk maxima per row
-    // as the selection kernel holds in shared memory
-    int se = 1;
-    while ((n_chunks + se - 1) / se > TAU_MAX_KEYS) ++se;
-    p->se = se;
-    p->n_c = (p->n_tiles + se - 1) / se * 8;
+    // pass A samples every se-th tile and keeps one lower bound per chunk of cw columns; its cost ~ 1/se, the candidate
+    // count ~ se.  Small item sets: every tile, 32-column chunks (train items knock out few of them); large ones:
+    // 64-column chunks and the smallest stride whose keys the selection kernel holds in shared memory.
+    int cw = 32, se = 1;
+    if ((int64_t)p->n_tiles * 4 > TAU_MAX_KEYS) {
+        cw = 64;
+        se = (int)(((int64_t)p->n_tiles * 2 + TAU_MAX_KEYS - 1) / TAU_MAX_KEYS);
+        const int want = env_int("PDA_TC_SE", 0);           // tuning knob: a larger stride (cheaper pass A, more candidates)
+        if (want > se) se = want;
+    }
+    p->cw = cw; p->se = se;
+    p->n_c = (p->n_tiles + se - 1) / se * (TN / cw);
+    // item-range splits: enough CTAs to fill the GPU in whole waves (one CTA per SM: shared memory), equal lengths
     const int m_tiles = (int)(p->M_pad / (TM * MR));
-    int splits = (148 * 2 + m_tiles - 1) / m_tiles;
-    if (splits < 1) splits = 1;
-    if (splits > p->n_tiles) splits = p->n_tiles;
-    p->tiles_per_split = (p->n_tiles + splits - 1) / splits;
+    const int n_sm = 148;
+    int s_min = (n_sm + m_tiles - 1) / m_tiles, s_max = p->n_tiles / se;
+    if (s_max < 1) s_max = 1;
+    if (s_min > s_max) s_min = s_max;
+    if (s_max > s_min + 40) s_max = s_min + 40;
+    int best_s = s_min; double best_eff = -1.0;
+    for (int s = s_min; s <= s_max; ++s) {
+        int tps = (p->n_tiles + s - 1) / s;
+        tps = (tps + se - 1) / se * se;
+        const int sp = (p->n_tiles + tps - 1) / tps;
+        const double waves = (double)m_tiles * sp / n_sm;
+        const double eff = waves / (double)(int64_t)(waves + 0.999999);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best_s = s; }
+        if (eff >= 0.96) break;
+    }
+    p->tiles_per_split = (p->n_tiles + best_s - 1) / best_s;
     p->tiles_per_split = (p->tiles_per_split + se - 1) / se * se;    // splits start on sampled tiles
     p->splits = (p->n_tiles + p->tiles_per_split - 1) / p->tiles_per_split;
-    // candidate lists: one segment per (item split, column group); twice the expected total as head-room
+    // candidate lists: one segment per (item split, column half); twice the expected total as head-room
     p->n_seg = p->splits * EPI_G;
     const int cap_total = a.N <= 262144 ? 1024 : 4096;
     p->seg_cap = ((2 * cap_total + p->n_seg - 1) / p->n_seg + 31) / 32 * 32;
@@ -824,6 +875,8 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     size_t o = 0;
     p->o_Ib = o; o += al256((size_t)p->N_pad * a.d * 2);
     p->o_Ub = o; o += al256((size_t)p->M_pad * a.d * 2);
+    p->o_Ix = o; o += al256((size_t)p->N_pad * KX * 2);
+    p->o_Ux = o; o += al256((size_t)p->M_pad * KX * 2);
     p->o_inorm = o; o += al256((size_t)p->N_pad * 4);
     p->o_unorm = o; o += al256((size_t)p->M_pad * 4);
     p->o_tnorm = o; o += al256((size_t)p->n_tiles * 4);
@@ -835,24 +888,67 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->o_flag = o; o += al256((size_t)p->M_pad * 4);
     p->o_frows = o; o += al256((size_t)p->M_pad * 4);
     p->o_fusers = o; o += al256((size_t)p->M_pad * 4);
-    p->o_nflag = o; o += 256;
+    p->o_nflag = o; o += 256;          // [0] rows without a certificate, [1] negative-pop flag
     return o;
 }
 
-template <int MODE, int PASS>
-static int launch_sweep(const CUtensorMap& tmA, const CUtensorMap& tmB, const SweepArgs& s, const TcPlan& p, int m_tiles,
-                        cudaStream_t st) {
+struct SweepMaps { CUtensorMap A, B, Ax, Bx; };
+
+template <int PASS>
+static int launch_sweep(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p, int m_tiles, cudaStream_t st) {
     using namespace tc;
     const int kblocks = s.d / KB;
-    const size_t a_bytes = (size_t)TM * 128 * kblocks * MR, b_bytes = (size_t)TN * 128 * kblocks;
-    int n_stages = (int)((204 * 1024 - a_bytes) / b_bytes);
-    if (n_stages > 4) n_stages = 4;
-    if (n_stages < 1) return 1;
-    const size_t smem = 1024 + a_bytes + (size_t)n_stages * b_bytes + 256 + 2048 + 64;
-    if (cudaFuncSetAttribute(tc_sweep_kernel<MODE, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    const size_t a_bytes = ((size_t)A_KB_BYTES * kblocks + (s.kx ? A_KX_BYTES : 0)) * MR;
+    const size_t b_bytes = (size_t)B_KB_BYTES * kblocks + (s.kx ? B_KX_BYTES : 0);
+    const size_t fixed = 1024 + 256 + 64;
+    int n_stages = (int)((227 * 1024 - fixed - a_bytes) / b_bytes);
+    if (n_stages > 6) n_stages = 6;
+    if (n_stages < 2) return 1;
+    const size_t smem = fixed + a_bytes + (size_t)n_stages * b_bytes;
+    if (cudaFuncSetAttribute(tc_sweep_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return 2;
     dim3 grid(m_tiles, p.splits);
-    tc_sweep_kernel<MODE, PASS><<<grid, NT, smem, st>>>(tmA, tmB, s, n_stages);
+    tc_sweep_kernel<PASS><<<grid, NT, smem, st>>>(tm.A, tm.B, tm.Ax, tm.Bx, s, n_stages);
+    return 0;
+}
+
+// prep shared by the filter pipeline and the diagnostics entry: bf16 operands, norms, tile maxima, tensor maps
+static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm, SweepArgs* s, cudaStream_t st) {
+    using namespace tc;
+    __nv_bfloat16* Ib = (__nv_bfloat16*)(b + p.o_Ib);
+    __nv_bfloat16* Ub = (__nv_bfloat16*)(b + p.o_Ub);
+    __nv_bfloat16* Ix = (__nv_bfloat16*)(b + p.o_Ix);
+    __nv_bfloat16* Ux = (__nv_bfloat16*)(b + p.o_Ux);
+    float* inorm = (float*)(b + p.o_inorm); float* unorm = (float*)(b + p.o_unorm); float* tnorm = (float*)(b + p.o_tnorm);
+    float* tcolmax = (float*)(b + p.o_tcolmax);
+    int32_t* nflag = (int32_t*)(b + p.o_nflag);
+    // the column term folded into the GEMM: pop ("condition": it also scales the item rows) or the column bias
+    const float* xcol = a.mode == 1 ? a.pop : a.col_bias;
+    const int kx = xcol ? 1 : 0;
+    cudaMemsetAsync(nflag, 0, 8, st);
+    tc_convert_rows_kernel<<<(unsigned)((p.N_pad * 32 + 255) / 256), 256, 0, st>>>(a.I, nullptr, a.N, p.N_pad, a.d,
+                                                                                  a.mode == 1 ? a.pop : nullptr, xcol, 0, Ib,
+                                                                                  kx ? Ix : nullptr, inorm, nflag + 1);
+    tc_convert_rows_kernel<<<(unsigned)((p.M_pad * 32 + 255) / 256), 256, 0, st>>>(a.U, a.users, a.M, p.M_pad, a.d, nullptr, nullptr, 1,
+                                                                                  Ub, kx ? Ux : nullptr, unorm, nflag + 1);
+    tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(inorm, p.n_tiles, tnorm, p.N_pad);
+    if (kx) tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(xcol, p.n_tiles, tcolmax, a.N);
+
+    if (make_map(&tm->A, Ub, p.M_pad, a.d, KB) || make_map(&tm->B, Ib, p.N_pad, a.d, KB)) return 3;
+    if (kx) {
+        if (make_map(&tm->Ax, Ux, p.M_pad, KX, KX) || make_map(&tm->Bx, Ix, p.N_pad, KX, KX)) return 3;
+    } else {
+        tm->Ax = tm->A; tm->Bx = tm->B;      // never dereferenced
+    }
+    memset(s, 0, sizeof(*s));
+    s->M = a.M; s->N = a.N; s->M_pad = p.M_pad; s->d = a.d; s->kx = kx; s->n_tiles = p.n_tiles;
+    s->tiles_per_split = p.tiles_per_split; s->se = p.se;
+    const float cA = 1.02f / 256.0f + (float)a.d / 2097152.0f, cB = (float)(a.d / 16 + 5) / 524288.0f;
+    s->cAB = cA + cB; s->cB = cB;
+    s->unorm = unorm; s->tile_inorm = tnorm; s->tile_col = kx ? tcolmax : nullptr;
+    s->cmax = (float*)(b + p.o_cmax); s->n_c = p.n_c; s->cw = p.cw;
+    s->tau = (float*)(b + p.o_tau); s->cand = (int32_t*)(b + p.o_cand); s->cnt = (int32_t*)(b + p.o_cnt);
+    s->n_seg = p.n_seg; s->seg_cap = p.seg_cap;
     return 0;
 }
 
@@ -862,50 +958,32 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, cudaS
     using namespace tc;
     if (!tc_supported(a)) return 1;
     char* b = (char*)scratch;
-    __nv_bfloat16* Ib = (__nv_bfloat16*)(b + p.o_Ib);
-    __nv_bfloat16* Ub = (__nv_bfloat16*)(b + p.o_Ub);
-    float* inorm = (float*)(b + p.o_inorm); float* unorm = (float*)(b + p.o_unorm); float* tnorm = (float*)(b + p.o_tnorm);
-    float* cmax = (float*)(b + p.o_cmax); float* tau = (float*)(b + p.o_tau);
-    int32_t* cnt = (int32_t*)(b + p.o_cnt); int32_t* cand = (int32_t*)(b + p.o_cand);
+    float* tau = (float*)(b + p.o_tau);
     int32_t* flag = (int32_t*)(b + p.o_flag); int32_t* frows = (int32_t*)(b + p.o_frows);
     int32_t* fusers = (int32_t*)(b + p.o_fusers); int32_t* nflag = (int32_t*)(b + p.o_nflag);
     const int m_tiles = (int)(p.M_pad / (TM * MR));
 
-    // prep
-    tc_convert_rows_kernel<<<(unsigned)((p.N_pad * 32 + 255) / 256), 256, 0, st>>>(a.I, nullptr, a.N, p.N_pad, a.d, Ib, inorm);
-    tc_convert_rows_kernel<<<(unsigned)((p.M_pad * 32 + 255) / 256), 256, 0, st>>>(a.U, a.users, a.M, p.M_pad, a.d, Ub, unorm);
-    tc_tile_norm_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(inorm, p.n_tiles, tnorm, p.N_pad);
-    float* tcolmax = (float*)(b + p.o_tcolmax);
-    if (a.mode == 1)
-        tc_tile_norm_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(a.pop, p.n_tiles, tcolmax, a.N);
-    cudaMemsetAsync(nflag, 0, 4, st);
-
-    CUtensorMap tmA, tmB;
-    if (make_map(&tmA, Ub, p.M_pad, a.d, TM) || make_map(&tmB, Ib, p.N_pad, a.d, TN)) return 3;
-
+    SweepMaps tm;
     SweepArgs s;
-    memset(&s, 0, sizeof(s));
-    s.M = a.M; s.N = a.N; s.M_pad = p.M_pad; s.d = a.d; s.n_tiles = p.n_tiles; s.tiles_per_split = p.tiles_per_split;
-    s.se = p.se;
-    s.c_err = 1.02f / 256.0f + (float)a.d / 2097152.0f;
-    s.unorm = unorm; s.tile_inorm = tnorm;
-    s.col = a.mode == 1 ? a.pop : a.col_bias;
-    s.tile_colmax = tcolmax;
-    s.cmax = cmax; s.n_c = p.n_c; s.tau = tau; s.cand = cand; s.cnt = cnt; s.n_seg = p.n_seg; s.seg_cap = p.seg_cap;
+    int rc = tc_prepare(a, b, p, &tm, &s, st);
+    if (rc) return rc;
 
-    int rc = a.mode == 1 ? launch_sweep<1, 0>(tmA, tmB, s, p, m_tiles, st) : launch_sweep<0, 0>(tmA, tmB, s, p, m_tiles, st);
+    rc = launch_sweep<0>(tm, s, p, m_tiles, st);
     if (rc) return 10 + rc;
-    tc_tau_select_kernel<<<(unsigned)((p.M_pad + 3) / 4), 128, (size_t)4 * (p.n_c + 256) * 4, st>>>(cmax, p.n_c, a.M, p.M_pad, p.se, a.users, a.mask_indptr,
-                                                                         a.mask_items, a.K, tau);
-    rc = a.mode == 1 ? launch_sweep<1, 1>(tmA, tmB, s, p, m_tiles, st) : launch_sweep<0, 1>(tmA, tmB, s, p, m_tiles, st);
+    const size_t tau_smem = (size_t)4 * (p.n_c + 256) * 4;
+    if (cudaFuncSetAttribute(tc_tau_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tau_smem) != cudaSuccess) return 15;
+    tc_tau_select_kernel<<<(unsigned)((p.M_pad + 3) / 4), 128, tau_smem, st>>>(s.cmax, p.n_c, a.M, p.M_pad, p.se, p.cw, a.users,
+                                                                               a.mask_indptr, a.mask_items, a.K, nflag + 1, tau);
+    rc = launch_sweep<1>(tm, s, p, m_tiles, st);
     if (rc) return 20 + rc;
 
     RescoreArgs r;
     memset(&r, 0, sizeof(r));
     r.U = a.U; r.I = a.I; r.M = a.M; r.N = a.N; r.users = a.users; r.mode = a.mode; r.pop = a.pop;
     r.col_bias = a.col_bias; r.mask_indptr = a.mask_indptr; r.mask_items = a.mask_items;
-    r.cand = cand; r.cnt = cnt; r.n_seg = p.n_seg; r.seg_cap = p.seg_cap; r.tiles_per_split = p.tiles_per_split;
+    r.cand = s.cand; r.cnt = s.cnt; r.n_seg = p.n_seg; r.seg_cap = p.seg_cap; r.tiles_per_split = p.tiles_per_split;
     r.tau = tau; r.K = a.K; r.rc = p.rc;
+    r.tile_col = s.tile_col; r.n_tiles = p.n_tiles;
     r.ids_out = a.ids_out; r.scores_out = a.scores_out; r.flag = flag;
     const size_t rs_smem = (size_t)4 * ((size_t)SORT_MAX * 8 + (size_t)p.rc * 8 + 1024 + (size_t)((p.n_seg + 2) / 2 * 2) * 4);
     if (a.d == 64) {
@@ -922,6 +1000,20 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, cudaS
     f.users = fusers; f.M_dev = nflag; f.out_rows = frows; f.dense_out = nullptr;
     if (launch_recommend_exact(f, st)) return 30;
     return 0;
+}
+
+// Diagnostics: the raw tensor-core accumulators v[M][N_pad] of the sweep (what pass A / pass B compare), so that a test
+// can check the operand layouts (TMA boxes, swizzles, UMMA descriptors) and the error bound E against fp64.
+int launch_tc_debug_dense(const EvalArgs& a, void* scratch, const TcPlan& p, float* dense, cudaStream_t st) {
+    using namespace tc;
+    if (!tc_supported(a)) return 1;
+    SweepMaps tm;
+    SweepArgs s;
+    int rc = tc_prepare(a, (char*)scratch, p, &tm, &s, st);
+    if (rc) return rc;
+    s.dense = dense; s.dense_ld = p.N_pad;
+    rc = launch_sweep<2>(tm, s, p, (int)(p.M_pad / (TM * MR)), st);
+    return rc ? 10 + rc : 0;
 }
 
 }  // namespace pda

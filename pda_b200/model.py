@@ -328,6 +328,18 @@ class PDAModel:
         return dict(zip(("rows", "rows_exact_fallback", "candidates", "max_candidates_row", "rows_overflow", "tile_stride",
                          "sampled_chunks", "item_splits"), (int(x) for x in out)))
 
+    def tc_debug_dense(self, batch_users, rec_type="main_branch", pos_pop=None, col_bias=None):
+        """Diagnostics: the raw tensor-core accumulators the filter compares (fp32 [len(users), n_items]) and the
+        coefficients (cAB, cB) of its error bound -- see pda_tc_debug_dense_host in include/pda_b200.h."""
+        u = _i32(batch_users)
+        pop = None if pos_pop is None else _f32(np.asarray(pos_pop).reshape(-1))
+        cb = None if col_bias is None else _f32(col_bias)
+        out = np.empty((len(u), self.n_items), dtype=np.float32)
+        coef = np.zeros(2, dtype=np.float32)
+        check(self.lib.pda_tc_debug_dense_host(self._h, ptr(u), len(u), REC_TYPES[rec_type], ptr(pop), ptr(cb), ptr(out),
+                                               ptr(coef)))
+        return out, (float(coef[0]), float(coef[1]))
+
     def testing(self, batch_users, items=None, model_type="main_branch", pos_pop=None):
         """train_new_api.py:642-669: dense fp32 [len(batch_users), n_items] ratings (no mask)."""
         if model_type not in ("main_branch", "condition"):

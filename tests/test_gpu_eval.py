@@ -112,6 +112,59 @@ def test_recommend_tensor_matches_oracle(pda, c_oracle, n_users, n_items, d, K, 
     m.close()
 
 
+@pytest.mark.parametrize("d,scale,zeros", [(64, 0.01, True), (128, 0.05, False), (64, 0.3, False)])
+def test_recommend_tensor_pop_dominated(pda, c_oracle, d, scale, zeros):
+    """An unfitted model: |s| << 1, so (elu(s)+1)*pop ~ pop and tau <= max pop -- the candidates come from the
+    'pop_j >= tau' branch of the upper bound (added by the rescoring kernel), not from the sweep alone."""
+    m, U, I, indptr, items, pop, rng = _setup(pda, 500, 9000, d, seed=7 + d, scale=scale)
+    pop = (rng.random(9000) ** 0.2).astype(np.float32)
+    if zeros:
+        pop[rng.random(9000) < 0.3] = 0.0
+    users = rng.permutation(500)[:480].astype(np.int32)
+    ids, sc = m.do_recommendation(users, None, "condition", pos_pop=pop, K=50, backend="tensor", return_scores=True)
+    st = m.tc_last_stats()
+    rid, rsc = c_oracle.recommend(U, I, users, "condition", 50, indptr, items, pop=pop)
+    assert np.array_equal(ids, rid), st
+    assert np.array_equal(bits(sc), bits(rsc))
+    assert st["rows_exact_fallback"] <= 0.05 * len(users), st
+    m.close()
+
+
+@pytest.mark.parametrize("d", [64, 128])
+@pytest.mark.parametrize("kind", ["main_branch", "condition", "bias"])
+def test_tensor_accumulators_within_error_bound(pda, d, kind):
+    """The raw TMEM accumulators (bf16 operands, pop / bias folded into the GEMM through the extra K block) against fp64:
+    checks the TMA boxes, both swizzles and the UMMA descriptors, and that the bound E of DESIGN.md 5.4 holds."""
+    m, U, I, indptr, items, pop, rng = _setup(pda, 640, 5000, d, seed=90 + d, scale=3.0)
+    users = rng.permutation(640)[:600].astype(np.int32)
+    bias = rng.normal(0, 0.3, 5000).astype(np.float32)
+    S = U[users].astype(np.float64) @ I.astype(np.float64).T
+    un = np.linalg.norm(U[users].astype(np.float64), axis=1)[:, None]
+    if kind == "condition":
+        v, (cAB, cB) = m.tc_debug_dense(users, "condition", pos_pop=pop)
+        want = (S + 1.0) * pop[None, :].astype(np.float64)
+        wn = np.linalg.norm(I.astype(np.float64) * pop[:, None], axis=1)[None, :]
+        xa = np.abs(pop)[None, :]
+    elif kind == "bias":
+        v, (cAB, cB) = m.tc_debug_dense(users, "main_branch", col_bias=bias)
+        want = S + bias[None, :]
+        wn = np.linalg.norm(I.astype(np.float64), axis=1)[None, :]
+        xa = np.abs(bias)[None, :]
+    else:
+        v, (cAB, cB) = m.tc_debug_dense(users, "main_branch")
+        want = S
+        wn = np.linalg.norm(I.astype(np.float64), axis=1)[None, :]
+        xa = np.zeros((1, 5000))
+    err = np.abs(v.astype(np.float64) - want)
+    E = cAB * un * wn + cB * xa + 1e-30
+    ratio = (err / E).max()
+    print("tensor accumulators: max |err| = %.3e, max err/E = %.3f, mean err/E = %.4f" % (err.max(), ratio, (err / E).mean()))
+    assert ratio <= 1.0, ratio
+    # the accumulators are real products, not noise inside a loose bound
+    assert err.max() <= 0.05 * np.abs(want).max()
+    m.close()
+
+
 def test_recommend_tensor_heavy_masks_and_bias(pda, c_oracle):
     """rows whose best items are all train items (the mask removes the top of the ranking) and the BPR(t)-pop bias."""
     from oracle import pda_oracle as po

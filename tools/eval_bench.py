@@ -53,11 +53,12 @@ def run(n_users, n_items, d, M, rec_type, deg, reps=5, backends=("exact", "tenso
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "douban"
+    bes = tuple(sys.argv[2].split(",")) if len(sys.argv) > 2 else ("exact", "tensor")
     if which == "douban":
         for rt in ("main_branch", "condition"):
             print(json.dumps({"shape": "douban-like 47890x26047 d=64 M=15974", "rec_type": rt,
-                              **run(47890, 26047, 64, 15974, rt, 138)}))
+                              **run(47890, 26047, 64, 15974, rt, 138, backends=bes)}))
     else:
         for rt in ("condition",):
             print(json.dumps({"shape": "synthetic 65536x1000000 d=128 M=16384", "rec_type": rt,
-                              **run(65536, 1000000, 128, 16384, rt, 24, reps=2)}))
+                              **run(65536, 1000000, 128, 16384, rt, 24, reps=2, backends=bes)}))
