@@ -58,7 +58,9 @@ constexpr int MR = 4;                               // user tiles resident per C
 constexpr int ACC = 4;                              // TMEM accumulator ring: ACC * TN = 512 columns
 constexpr int EPI_G = 2;                            // epilogue warp groups: each owns TN / EPI_G columns of every tile
 constexpr int EPI_COLS = TN / EPI_G;                // 64 columns per thread and tile = two tcgen05.ld x32
-constexpr int NT = 128 + 128 * EPI_G;               // warps: 0 TMA, 1 MMA, 2-3 idle, then 4 * EPI_G epilogue warps
+constexpr int EPI_WARPS = 4 * EPI_G;                // warps 0-7: epilogue (TMEM lane quadrant = warp % 4, column half = warp / 4)
+constexpr int TMA_WARP = EPI_WARPS, MMA_WARP = EPI_WARPS + 1;   // the highest warp ids: the issue arbiter prefers them
+constexpr int NT = 32 * (EPI_WARPS + 2);
 constexpr uint32_t A_KB_BYTES = TM * 128u, B_KB_BYTES = TN * 128u;      // one K block of an A / B tile
 constexpr uint32_t A_KX_BYTES = TM * 32u, B_KX_BYTES = TN * 32u;        // the extra block
 
@@ -67,6 +69,19 @@ constexpr uint32_t A_KX_BYTES = TM * 32u, B_KX_BYTES = TN * 32u;        // the e
 // ------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// one lane of a converged warp (elect.sync): the branch stays warp-uniform for the compiler, so the operands of the
+// TMA / MMA instructions inside it live in uniform registers and no per-lane waterfall loop is generated
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 rx;\n\t"
+        ".reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t"
+        "}" : "+r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
@@ -139,6 +154,10 @@ __device__ __forceinline__ uint64_t make_desc_sw32(uint32_t saddr) {
     return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(256 >> 4) << 32) | ((uint64_t)1 << 46) |
            ((uint64_t)6 << 61);
 }
+// the same descriptors as (high word, low word): high = SBO >> 4 | version 1 (bit 46) | layout type (bit 61)
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_HI_SW32 = (256u >> 4) | (1u << 14) | (6u << 29);
+__device__ __forceinline__ uint64_t make_desc_hl(uint32_t hi, uint32_t lo) { return ((uint64_t)hi << 32) | lo; }
 // kind::f16: D = F32 (bit 4), A = B = BF16 (bits 7, 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
 
@@ -204,6 +223,32 @@ __global__ void __launch_bounds__(256) tc_tile_max_kernel(const float* __restric
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
     if (lane == 0) tmax[t] = m;
+}
+
+// per 128-item tile of pop (>= 0): the largest value, its item id, the second largest value (0 when absent)
+__global__ void __launch_bounds__(256) tc_tile_top2_kernel(const float* __restrict__ v, int64_t n_tiles, int64_t n,
+                                                           float* __restrict__ t1, int32_t* __restrict__ targ,
+                                                           float* __restrict__ t2) {
+    const int lane = threadIdx.x & 31;
+    const int64_t t = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (t >= n_tiles) return;
+    float m1 = -1.0f, m2 = -1.0f;
+    int j1 = 0;
+    for (int c = lane; c < tc::TN; c += 32) {
+        const int64_t j = t * tc::TN + c;
+        if (j < n) {
+            const float x = v[j];
+            if (x > m1) { m2 = m1; m1 = x; j1 = (int)j; } else if (x > m2) m2 = x;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const float o1 = __shfl_xor_sync(0xffffffffu, m1, off), o2 = __shfl_xor_sync(0xffffffffu, m2, off);
+        const int oj = __shfl_xor_sync(0xffffffffu, j1, off);
+        if (o1 > m1 || (o1 == m1 && oj < j1)) { m2 = fmaxf(m1, o2); m1 = o1; j1 = oj; }
+        else m2 = fmaxf(m2, o1);
+    }
+    if (lane == 0) { t1[t] = fmaxf(m1, 0.f); targ[t] = j1; t2[t] = fmaxf(m2, 0.f); }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -284,20 +329,20 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float thr, i
 
 }  // namespace tc
 
-template <int PASS>
+template <int PASS, int KBLK, int KXT>      // KBLK = d / 64 K blocks, KXT = 1: the 16-column extra K block is present
 __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmAx,
                                                               const __grid_constant__ CUtensorMap tmBx, SweepArgs a,
                                                               int n_stages) {
     using namespace tc;
+    static_assert(MR == ACC, "accumulator index = resident user tile index");
     extern __shared__ unsigned char smem_raw[];
     // 1024 B alignment for the 128B-swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int kblocks = a.d / KB;
-    const uint32_t a1_bytes = A_KB_BYTES * kblocks + (a.kx ? A_KX_BYTES : 0u);     // one user tile: K blocks + extra block
-    const uint32_t a_bytes = a1_bytes * MR;                                        // MR user tiles stay resident for the whole sweep
-    const uint32_t b_bytes = B_KB_BYTES * kblocks + (a.kx ? B_KX_BYTES : 0u);      // one B stage
+    constexpr uint32_t a1_bytes = A_KB_BYTES * KBLK + (KXT ? A_KX_BYTES : 0u);     // one user tile: K blocks + extra block
+    constexpr uint32_t a_bytes = a1_bytes * MR;                                    // MR user tiles stay resident for the whole sweep
+    constexpr uint32_t b_bytes = B_KB_BYTES * KBLK + (KXT ? B_KX_BYTES : 0u);      // one B stage
     unsigned char* sA = smem;
     unsigned char* sB = smem + a_bytes;
     unsigned char* tail_p = sB + (size_t)n_stages * b_bytes;
@@ -318,71 +363,89 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int s = 0; s < ACC; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, 4 * EPI_G); }
+        for (int s = 0; s < ACC; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, EPI_WARPS); }
         mbar_init(bar_afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) tmem_alloc(smem_u32(tmem_slot), ACC * TN);
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), ACC * TN);
     fence_before();
     __syncthreads();
     fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    // Every B tile is multiplied with the MR resident user tiles in turn: sub-step sub = i * MR + mr uses accumulator
-    // sub % ACC, so the epilogue of up to ACC - 1 earlier sub-steps overlaps the MMAs of the current one.
-    if (warp == 0) {
+    // Every B tile is multiplied with the MR resident user tiles in turn; user tile mr accumulates into TMEM stage mr
+    // (phase = tile parity), so the epilogue of up to ACC - 1 earlier sub-steps overlaps the MMAs of the current one.
+    // The TMA and MMA warps run converged; one elected lane issues (see elect_one).
+    if (warp == TMA_WARP) {
         // ===== TMA producer =====
-        if (lane == 0 && n_my > 0) {
-            mbar_expect_tx(bar_afull, a_bytes);
-            for (int mr = 0; mr < MR; ++mr) {
-                unsigned char* at = sA + (size_t)mr * a1_bytes;
-                const int r0 = (m_blk * MR + mr) * TM;
-                for (int kb = 0; kb < kblocks; ++kb) tma_load_2d(smem_u32(at + (size_t)kb * A_KB_BYTES), &tmA, bar_afull, kb * KB, r0);
-                if (a.kx) tma_load_2d(smem_u32(at + (size_t)kblocks * A_KB_BYTES), &tmAx, bar_afull, 0, r0);
-            }
-            for (int i = 0; i < n_my; ++i) {
-                const int s = i % n_stages, ph = (i / n_stages) & 1;
-                mbar_wait(bar_empty + 8 * s, ph ^ 1);
-                mbar_expect_tx(bar_full + 8 * s, b_bytes);
-                const int t = t_first + i * step;
-                unsigned char* bt = sB + (size_t)s * b_bytes;
-                for (int kb = 0; kb < kblocks; ++kb)
-                    tma_load_2d(smem_u32(bt + (size_t)kb * B_KB_BYTES), &tmB, bar_full + 8 * s, kb * KB, t * TN);
-                if (a.kx) tma_load_2d(smem_u32(bt + (size_t)kblocks * B_KB_BYTES), &tmBx, bar_full + 8 * s, 0, t * TN);
-            }
-        }
-    } else if (warp == 1) {
-        // ===== MMA issuer =====
-        if (lane == 0 && n_my > 0) {
-            mbar_wait(bar_afull, 0);
-            for (int i = 0; i < n_my; ++i) {
-                const int s = i % n_stages, ph = (i / n_stages) & 1;
-                mbar_wait(bar_full + 8 * s, ph);
-                unsigned char* bt = sB + (size_t)s * b_bytes;
-                for (int mr = 0; mr < MR; ++mr) {
-                    const int sub = i * MR + mr, acc = sub % ACC, aph = (sub / ACC) & 1;
-                    mbar_wait(bar_tempty + 8 * acc, aph ^ 1);
-                    fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)acc * TN;
-                    unsigned char* at = sA + (size_t)mr * a1_bytes;
-                    for (int kb = 0; kb < kblocks; ++kb) {
-                        const uint64_t ad = make_desc(smem_u32(at + (size_t)kb * A_KB_BYTES));
-                        const uint64_t bd = make_desc(smem_u32(bt + (size_t)kb * B_KB_BYTES));
+        if (n_my > 0) {
+            if (elect_one()) {
+                mbar_expect_tx(bar_afull, a_bytes);
 #pragma unroll
-                        for (int k = 0; k < KB / 16; ++k)    // UMMA K = 16 bf16 = 32 B inside the 128 B swizzle row
-                            umma_bf16(d_tmem, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), IDESC, (kb | k) ? 1u : 0u);
-                    }
-                    if (a.kx)                                // + x_j: (1, 1, 1, 0...) . (x_hi, x_mid, x_lo, 0...)
-                        umma_bf16(d_tmem, make_desc_sw32(smem_u32(at + (size_t)kblocks * A_KB_BYTES)),
-                                  make_desc_sw32(smem_u32(bt + (size_t)kblocks * B_KB_BYTES)), IDESC, 1u);
-                    if (mr == MR - 1) umma_commit(bar_empty + 8 * s);   // B stage may be refilled once these MMAs retire
-                    umma_commit(bar_tfull + 8 * acc);                   // accumulator ready for the epilogue
+                for (int mr = 0; mr < MR; ++mr) {
+                    const uint32_t at = smem_u32(sA) + (uint32_t)mr * a1_bytes;
+                    const int r0 = (m_blk * MR + mr) * TM;
+#pragma unroll
+                    for (int kb = 0; kb < KBLK; ++kb) tma_load_2d(at + (uint32_t)kb * A_KB_BYTES, &tmA, bar_afull, kb * KB, r0);
+                    if (KXT) tma_load_2d(at + (uint32_t)KBLK * A_KB_BYTES, &tmAx, bar_afull, 0, r0);
                 }
             }
+            __syncwarp();
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < n_my; ++i) {
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);
+                if (elect_one()) {
+                    mbar_expect_tx(bar_full + 8 * s, b_bytes);
+                    const int t = t_first + i * step;
+                    const uint32_t bt = smem_u32(sB) + (uint32_t)s * b_bytes;
+#pragma unroll
+                    for (int kb = 0; kb < KBLK; ++kb) tma_load_2d(bt + (uint32_t)kb * B_KB_BYTES, &tmB, bar_full + 8 * s, kb * KB, t * TN);
+                    if (KXT) tma_load_2d(bt + (uint32_t)KBLK * B_KB_BYTES, &tmBx, bar_full + 8 * s, 0, t * TN);
+                }
+                __syncwarp();
+                if (++s == n_stages) { s = 0; ph ^= 1; }
+            }
         }
-    } else if (warp >= 4) {
+    } else if (warp == MMA_WARP) {
+        // ===== MMA issuer: descriptors = loop-invariant low word + compile-time offsets (16 B units) =====
+        if (n_my > 0) {
+            mbar_wait(bar_afull, 0);
+            const uint32_t a_lo = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int i = 0; i < n_my; ++i) {
+                mbar_wait(bar_full + 8 * s, ph);
+                const uint32_t b_lo = b_lo0 + (uint32_t)s * (b_bytes >> 4);
+                const uint32_t aph = (uint32_t)i & 1u;
+#pragma unroll
+                for (int mr = 0; mr < MR; ++mr) {
+                    mbar_wait(bar_tempty + 8 * mr, aph ^ 1u);
+                    fence_after();
+                    if (elect_one()) {
+                        const uint32_t d_tmem = tmem_base + (uint32_t)mr * TN;
+                        const uint32_t am = a_lo + (uint32_t)mr * (a1_bytes >> 4);
+#pragma unroll
+                        for (int kb = 0; kb < KBLK; ++kb)
+#pragma unroll
+                            for (int k = 0; k < KB / 16; ++k)    // UMMA K = 16 bf16 = 32 B inside the 128 B swizzle row
+                                umma_bf16(d_tmem, make_desc_hl(DESC_HI_SW128, am + kb * (A_KB_BYTES >> 4) + k * 2),
+                                          make_desc_hl(DESC_HI_SW128, b_lo + kb * (B_KB_BYTES >> 4) + k * 2), IDESC, (kb | k) ? 1u : 0u);
+                        if (KXT)                                 // + x_j: (1, 1, 1, 0...) . (x_hi, x_mid, x_lo, 0...)
+                            umma_bf16(d_tmem, make_desc_hl(DESC_HI_SW32, am + KBLK * (A_KB_BYTES >> 4)),
+                                      make_desc_hl(DESC_HI_SW32, b_lo + KBLK * (B_KB_BYTES >> 4)), IDESC, 1u);
+                        if (mr == MR - 1) umma_commit(bar_empty + 8 * s);   // B stage may be refilled once these MMAs retire
+                        umma_commit(bar_tfull + 8 * mr);                    // accumulator ready for the epilogue
+                    }
+                    __syncwarp();
+                }
+                if (++s == n_stages) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
         // ===== epilogue: thread = (row 32q + lane of each resident user tile, column half h of every tile) =====
-        const int q = warp & 3, h = (warp - 4) >> 2;
+        const int q = warp & 3, h = warp >> 2;
         // pass B: this thread owns segment (split, h) of each of its rows' candidate lists -> no atomics
         const int seg = blockIdx.y * EPI_G + h;
         int64_t row[MR];
@@ -399,16 +462,22 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             n_local[mr] = 0;
         }
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * EPI_COLS);
+        float tn_next = n_my > 0 ? __ldg(a.tile_inorm + t_first) : 0.f;
+        float tcol_next = (KXT && n_my > 0) ? __ldg(a.tile_col + t_first) : 0.f;
         for (int i = 0; i < n_my; ++i) {
             const int t = t_first + i * step;
             const int64_t j0 = (int64_t)t * TN + h * EPI_COLS;       // first column of this thread's half
-            const float tn = __ldg(a.tile_inorm + t);
-            const float tcol = a.tile_col ? __ldg(a.tile_col + t) : 0.f;
+            const float tn = tn_next, tcol = tcol_next;
+            if (i + 1 < n_my) {                                      // the next tile's bound terms: latency off the critical path
+                tn_next = __ldg(a.tile_inorm + t + step);
+                if (KXT) tcol_next = __ldg(a.tile_col + t + step);
+            }
             const float eb = fmaf(a.cB, tcol, 1e-30f);
             const bool tail = j0 + EPI_COLS > a.N;
 #pragma unroll
             for (int mr = 0; mr < MR; ++mr) {
-                const int sub = i * MR + mr, acc = sub % ACC, aph = (sub / ACC) & 1;
+                const int acc = mr;
+                const uint32_t aph = (uint32_t)i & 1u;
                 float E = fmaf(unAB[mr], tn, eb);                    // |v_j - its real-number meaning| <= E on this tile
                 E = fmaf(E, 2e-6f, E);
                 mbar_wait(bar_tfull + 8 * acc, aph);
@@ -449,7 +518,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
     }
     fence_before();
     __syncthreads();
-    if (warp == 1) { __syncwarp(); fence_after(); tmem_dealloc(tmem_base, ACC * TN); }
+    if (warp == MMA_WARP) { __syncwarp(); fence_after(); tmem_dealloc(tmem_base, ACC * TN); }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -580,36 +649,70 @@ struct RescoreArgs {
     const float* tau;
     int K;
     int rc;             // per-row capacity of the compacted candidate list in shared memory
-    const float* tile_col; int n_tiles;     // mode 1: max pop of every 128-item tile (the pop branch of the upper bound)
+    // mode 1, the pop branch of the upper bound: per 128-item tile the largest pop, its item, the second largest
+    const float* tile_col; const int32_t* tile_arg; const float* tile_col2; int n_tiles;
     int32_t* ids_out; float* scores_out;
     int32_t* flag;      // [M] 1 = not certified
 };
 
 constexpr int SORT_MAX = 256;
+constexpr int HOT_CAP = 2 * SORT_MAX;       // hot-tile list of a row (lives in the sort buffer, which is used later)
 
-//  1. the row's candidate segments -> one compact id list in shared memory
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// per-warp shared memory of the rescoring kernel
+__host__ __device__ inline size_t rescore_warp_bytes(int D, int RC, int n_seg) {
+    return (size_t)33 * (D + 4) * 4 + (size_t)RC * 8 + (size_t)((n_seg + 4) / 4 * 4) * 4;
+}
+
+// is item j among the sweep's candidates of this row?  (segment sg of the compact list, ascending ids)
+__device__ __forceinline__ bool in_segment(const int* cid, const int* soff, int sg, int j) {
+    const int send = soff[sg + 1];
+    int l = soff[sg], r = send;
+    while (l < r) {
+        const int mid = (l + r) >> 1;
+        if (cid[mid] < j) l = mid + 1; else r = mid;
+    }
+    return l < send && cid[l] == j;
+}
+
+//  1. the row's candidate segments -> one compact id list in shared memory (+ the pop-branch items, mode 1)
 //  2. train items out: every masked item lives in exactly one segment (ascending ids) -> binary search there
-//  3. exact fp32 score (the sequential-k spec) + transform of every remaining candidate
+//  3. exact fp32 score (the sequential-k spec) + transform of every remaining candidate: item rows are staged 32 at a
+//     time with cp.async (every row one coalesced request, all in flight together), then lane l runs the sequential
+//     chain of candidate l out of shared memory
 //  4. K-th largest exact score by radix select, survivors (>= it) bitonic-sorted by (score desc, id asc)
 //  5. certificate: no overflow and >= K unmasked candidates with exact score >= tau
 template <int D>
 __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
-    extern __shared__ __align__(8) unsigned char rs_smem[];
+    extern __shared__ __align__(16) unsigned char rs_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int RC = a.rc;
-    // per warp: sortbuf[256] u64 | cid[RC] | ckey[RC] | hist[256] | soff[n_seg + 1]
-    const size_t per_warp = (size_t)SORT_MAX * 8 + (size_t)RC * 8 + 1024 + (size_t)((a.n_seg + 2) / 2 * 2) * 4;
+    constexpr int S = D + 4;                // staged row stride in floats: (S / 4) odd -> conflict-free 128-bit reads
+    // per warp: stage[32][S] + us[S] | cid[RC] | ckey[RC] | soff[n_seg + 1]; the sort buffer (= hot-tile list of step
+    // 1b) and the histogram alias the first 3 KB of the stage: they are used before / after step 3 only
+    static_assert(32 * S * 4 >= SORT_MAX * 8 + 1024, "sort buffer + histogram must fit below the user row");
+    const size_t per_warp = rescore_warp_bytes(D, RC, a.n_seg);
     unsigned char* base = rs_smem + (size_t)w * per_warp;
+    float* stage = reinterpret_cast<float*>(base);
+    float* us = stage + 32 * S;
     unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(base);
-    int* cid = reinterpret_cast<int*>(base + (size_t)SORT_MAX * 8);
-    uint32_t* ckey = reinterpret_cast<uint32_t*>(base + (size_t)SORT_MAX * 8 + (size_t)RC * 4);
-    int* hist = reinterpret_cast<int*>(base + (size_t)SORT_MAX * 8 + (size_t)RC * 8);
-    int* soff = hist + 256;
+    int* hist = reinterpret_cast<int*>(base + (size_t)SORT_MAX * 8);
+    unsigned char* b2 = base + (size_t)33 * S * 4;
+    int* cid = reinterpret_cast<int*>(b2);
+    uint32_t* ckey = reinterpret_cast<uint32_t*>(b2 + (size_t)RC * 4);
+    int* soff = reinterpret_cast<int*>(b2 + (size_t)RC * 8);
     const int64_t row = (int64_t)blockIdx.x * 4 + w;
     if (row >= a.M) return;
     const int K = a.K;
     const int u = a.users[row];
     const float* ur = a.U + (int64_t)u * D;
+    if (lane < D / 4) cp_async16(us + 4 * lane, ur + 4 * lane);       // the user row: read by every lane (broadcast)
 
     // 1. compact
     bool overflow = false;
@@ -630,7 +733,7 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
     overflow = __any_sync(0xffffffffu, overflow) || tot > RC;
     if (lane == 0) soff[a.n_seg] = tot;
     __syncwarp();
-    if (overflow) { if (lane == 0) a.flag[row] = 1; return; }
+    if (overflow) { if (lane == 0) a.flag[row] = 1; cp_async_wait_all(); return; }
     for (int sg = 0; sg < a.n_seg; ++sg) {
         const int o = soff[sg], nn = soff[sg + 1] - o;
         const int32_t* cl = a.cand + (row * a.n_seg + sg) * a.seg_cap;
@@ -639,42 +742,69 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
     __syncwarp();
 
     // 1b. "condition": f(s) * pop <= max((s + 1) * pop, pop), and the sweep only tests the first branch.  Items with
-    //     pop_j >= tau are candidates by the second one whatever the user: scan the tiles whose largest pop reaches tau
-    //     (none at all once tau > max pop, the fitted-model case), skip what the sweep already delivered.
+    //     pop_j >= tau are candidates by the second one whatever the user.  Tiles whose largest pop reaches tau are
+    //     listed first (none at all once tau > max pop, the fitted-model case); a tile with a single such item (its
+    //     second largest pop is below tau) is settled by one lane, the others are scanned by the warp.
     int n_extra = 0;
+    const float tau = a.tau[row];
     if (a.mode == 1) {
-        const float tl = tc::tau_lower(a.tau[row]);
-        for (int tb = 0; tb < a.n_tiles && tot + n_extra <= RC; tb += 32) {
-            const int t = tb + lane;
-            unsigned bal = __ballot_sync(0xffffffffu, t < a.n_tiles && __ldg(a.tile_col + t) >= tl);
-            while (bal) {
-                const int th = tb + __ffs(bal) - 1;
-                bal &= bal - 1;
+        const float tl = tc::tau_lower(tau);
+        int* hot = reinterpret_cast<int*>(sortbuf);
+        int n_hot = 0;
+        for (int tb = 0; tb < a.n_tiles; tb += 128) {
+            bool h[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) { const int t = tb + q * 32 + lane; h[q] = t < a.n_tiles && __ldg(a.tile_col + t) >= tl; }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const unsigned bal = __ballot_sync(0xffffffffu, h[q]);
+                if (h[q]) {
+                    const int pos = n_hot + __popc(bal & ((1u << lane) - 1u));
+                    if (pos < HOT_CAP) hot[pos] = tb + q * 32 + lane;
+                }
+                n_hot += __popc(bal);
+            }
+        }
+        if (n_hot > HOT_CAP) { if (lane == 0) a.flag[row] = 1; cp_async_wait_all(); return; }
+        __syncwarp();
+        for (int i0 = 0; i0 < n_hot && tot + n_extra <= RC; i0 += 32) {
+            const int i = i0 + lane;
+            int th = 0, j = 0;
+            bool multi = false, c = false;
+            if (i < n_hot) {
+                th = hot[i];
+                multi = __ldg(a.tile_col2 + th) >= tl;
+                if (!multi) {
+                    j = __ldg(a.tile_arg + th);
+                    c = !in_segment(cid, soff, (th / a.tiles_per_split) * tc::EPI_G + (j % tc::TN) / tc::EPI_COLS, j);
+                }
+            }
+            unsigned bl = __ballot_sync(0xffffffffu, c);
+            if (c) {
+                const int pos = tot + n_extra + __popc(bl & ((1u << lane) - 1u));
+                if (pos < RC) cid[pos] = j;
+            }
+            n_extra += __popc(bl);
+            unsigned mb = __ballot_sync(0xffffffffu, multi);
+            while (mb && tot + n_extra <= RC) {
+                const int tm = __shfl_sync(0xffffffffu, th, __ffs(mb) - 1);
+                mb &= mb - 1;
 #pragma unroll
                 for (int k = 0; k < tc::TN / 32; ++k) {
                     const int cidx = k * 32 + lane;
-                    const int64_t j = (int64_t)th * tc::TN + cidx;
-                    bool c = j < a.N && __ldg(a.pop + j) >= tl;
-                    if (c) {
-                        const int sg = (th / a.tiles_per_split) * tc::EPI_G + cidx / tc::EPI_COLS;
-                        const int send = soff[sg + 1];
-                        int l = soff[sg], r = send;
-                        while (l < r) {
-                            const int mid = (l + r) >> 1;
-                            if (cid[mid] < (int)j) l = mid + 1; else r = mid;
-                        }
-                        c = !(l < send && cid[l] == (int)j);
+                    const int64_t jj = (int64_t)tm * tc::TN + cidx;
+                    bool cc = jj < a.N && __ldg(a.pop + jj) >= tl;
+                    if (cc) cc = !in_segment(cid, soff, (tm / a.tiles_per_split) * tc::EPI_G + cidx / tc::EPI_COLS, (int)jj);
+                    bl = __ballot_sync(0xffffffffu, cc);
+                    if (cc) {
+                        const int pos = tot + n_extra + __popc(bl & ((1u << lane) - 1u));
+                        if (pos < RC) cid[pos] = (int)jj;
                     }
-                    const unsigned b2 = __ballot_sync(0xffffffffu, c);
-                    if (c) {
-                        const int pos = tot + n_extra + __popc(b2 & ((1u << lane) - 1u));
-                        if (pos < RC) cid[pos] = (int)j;
-                    }
-                    n_extra += __popc(b2);
+                    n_extra += __popc(bl);
                 }
             }
         }
-        if (tot + n_extra > RC) { if (lane == 0) a.flag[row] = 1; return; }
+        if (tot + n_extra > RC) { if (lane == 0) a.flag[row] = 1; cp_async_wait_all(); return; }
         __syncwarp();
     }
 
@@ -697,26 +827,39 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
         }
         __syncwarp();
     }
-
     tot += n_extra;
 
-    // 3. exact scores
-    const float tau = a.tau[row];
+    // 3. exact scores, 32 candidates per round
     int n_cert = 0;
-    for (int c = lane; c < tot; c += 32) {
-        const int j = cid[c];
+    cp_async_wait_all();
+    for (int c0 = 0; c0 < tot; c0 += 32) {
+        const int nb = min(32, tot - c0);
+        if (D == 128) {
+            for (int r = 0; r < nb; ++r) {
+                const int j = cid[c0 + r];
+                if (j >= 0) cp_async16(stage + r * S + 4 * lane, a.I + (int64_t)j * D + 4 * lane);
+            }
+        } else {
+            for (int r = 0; r < nb; r += 2) {
+                const int rr = r + (lane >> 4);
+                const int j = rr < nb ? cid[c0 + rr] : -1;
+                if (j >= 0) cp_async16(stage + rr * S + 4 * (lane & 15), a.I + (int64_t)j * D + 4 * (lane & 15));
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+        const int c = c0 + lane;
+        const int j = c < tot ? cid[c] : -1;
         uint32_t key = 0;
         if (j >= 0) {
-            const float* ir = a.I + (int64_t)j * D;
-            float4 iv[D / 4];
-#pragma unroll
-            for (int k = 0; k < D / 4; ++k) iv[k] = ldg_f4(ir + 4 * k);     // the whole row in flight at once
+            const float* ir = stage + lane * S;
             float acc = 0.0f;
-#pragma unroll
+#pragma unroll 8
             for (int k = 0; k < D / 4; ++k) {
-                const float4 uv = ldg_f4(ur + 4 * k);
-                acc = fadd(acc, fmul(uv.x, iv[k].x)); acc = fadd(acc, fmul(uv.y, iv[k].y));
-                acc = fadd(acc, fmul(uv.z, iv[k].z)); acc = fadd(acc, fmul(uv.w, iv[k].w));
+                const float4 iv = *reinterpret_cast<const float4*>(ir + 4 * k);
+                const float4 uv = *reinterpret_cast<const float4*>(us + 4 * k);
+                acc = fadd(acc, fmul(uv.x, iv.x)); acc = fadd(acc, fmul(uv.y, iv.y));
+                acc = fadd(acc, fmul(uv.z, iv.z)); acc = fadd(acc, fmul(uv.w, iv.w));
             }
             float y;
             if (a.mode == 1) y = fmul(elu_p1(acc), __ldg(a.pop + j));
@@ -725,7 +868,8 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
             if (key == 0u) key = 1u;          // (only -NaN patterns map to 0) keep 0 for "not a candidate"
             n_cert += y >= tau;
         }
-        ckey[c] = key;
+        if (c < tot) ckey[c] = key;
+        __syncwarp();                          // the stage is rewritten by the next round
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) n_cert += __shfl_xor_sync(0xffffffffu, n_cert, off);
@@ -881,6 +1025,8 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->o_unorm = o; o += al256((size_t)p->M_pad * 4);
     p->o_tnorm = o; o += al256((size_t)p->n_tiles * 4);
     p->o_tcolmax = o; o += al256((size_t)p->n_tiles * 4);
+    p->o_targ = o; o += al256((size_t)p->n_tiles * 4);
+    p->o_tcol2 = o; o += al256((size_t)p->n_tiles * 4);
     p->o_cmax = o; o += al256((size_t)p->n_c * p->M_pad * 4);
     p->o_tau = o; o += al256((size_t)p->M_pad * 4);
     p->o_cnt = o; o += al256((size_t)p->M_pad * p->n_seg * 4);
@@ -894,8 +1040,8 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
 
 struct SweepMaps { CUtensorMap A, B, Ax, Bx; };
 
-template <int PASS>
-static int launch_sweep(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p, int m_tiles, cudaStream_t st) {
+template <int PASS, int KBLK, int KXT>
+static int launch_sweep_t(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p, int m_tiles, cudaStream_t st) {
     using namespace tc;
     const int kblocks = s.d / KB;
     const size_t a_bytes = ((size_t)A_KB_BYTES * kblocks + (s.kx ? A_KX_BYTES : 0)) * MR;
@@ -905,11 +1051,17 @@ static int launch_sweep(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p
     if (n_stages > 6) n_stages = 6;
     if (n_stages < 2) return 1;
     const size_t smem = fixed + a_bytes + (size_t)n_stages * b_bytes;
-    if (cudaFuncSetAttribute(tc_sweep_kernel<PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_sweep_kernel<PASS, KBLK, KXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return 2;
     dim3 grid(m_tiles, p.splits);
-    tc_sweep_kernel<PASS><<<grid, NT, smem, st>>>(tm.A, tm.B, tm.Ax, tm.Bx, s, n_stages);
+    tc_sweep_kernel<PASS, KBLK, KXT><<<grid, NT, smem, st>>>(tm.A, tm.B, tm.Ax, tm.Bx, s, n_stages);
     return 0;
+}
+
+template <int PASS>
+static int launch_sweep(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p, int m_tiles, cudaStream_t st) {
+    if (s.d == 64) return s.kx ? launch_sweep_t<PASS, 1, 1>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 1, 0>(tm, s, p, m_tiles, st);
+    return s.kx ? launch_sweep_t<PASS, 2, 1>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 2, 0>(tm, s, p, m_tiles, st);
 }
 
 // prep shared by the filter pipeline and the diagnostics entry: bf16 operands, norms, tile maxima, tensor maps
@@ -932,7 +1084,12 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
     tc_convert_rows_kernel<<<(unsigned)((p.M_pad * 32 + 255) / 256), 256, 0, st>>>(a.U, a.users, a.M, p.M_pad, a.d, nullptr, nullptr, 1,
                                                                                   Ub, kx ? Ux : nullptr, unorm, nflag + 1);
     tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(inorm, p.n_tiles, tnorm, p.N_pad);
-    if (kx) tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(xcol, p.n_tiles, tcolmax, a.N);
+    if (a.mode == 1)
+        tc_tile_top2_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(xcol, p.n_tiles, a.N, tcolmax,
+                                                                                             (int32_t*)(b + p.o_targ),
+                                                                                             (float*)(b + p.o_tcol2));
+    else if (kx)
+        tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(xcol, p.n_tiles, tcolmax, a.N);
 
     if (make_map(&tm->A, Ub, p.M_pad, a.d, KB) || make_map(&tm->B, Ib, p.N_pad, a.d, KB)) return 3;
     if (kx) {
@@ -983,9 +1140,10 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, cudaS
     r.col_bias = a.col_bias; r.mask_indptr = a.mask_indptr; r.mask_items = a.mask_items;
     r.cand = s.cand; r.cnt = s.cnt; r.n_seg = p.n_seg; r.seg_cap = p.seg_cap; r.tiles_per_split = p.tiles_per_split;
     r.tau = tau; r.K = a.K; r.rc = p.rc;
-    r.tile_col = s.tile_col; r.n_tiles = p.n_tiles;
+    r.tile_col = s.tile_col; r.tile_arg = (const int32_t*)(b + p.o_targ); r.tile_col2 = (const float*)(b + p.o_tcol2);
+    r.n_tiles = p.n_tiles;
     r.ids_out = a.ids_out; r.scores_out = a.scores_out; r.flag = flag;
-    const size_t rs_smem = (size_t)4 * ((size_t)SORT_MAX * 8 + (size_t)p.rc * 8 + 1024 + (size_t)((p.n_seg + 2) / 2 * 2) * 4);
+    const size_t rs_smem = 4 * rescore_warp_bytes(a.d, p.rc, p.n_seg);
     if (a.d == 64) {
         cudaFuncSetAttribute(tc_rescore_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem);
         tc_rescore_kernel<64><<<(unsigned)((a.M + 3) / 4), 128, rs_smem, st>>>(r);
