@@ -878,7 +878,7 @@ static int do_recommend(pda_model* m, const EvalArgs& a, int backend, cudaStream
         tc_scratch_bytes(blk, &plan);
         m->tc_last_plan = plan; m->tc_last_M = blk.M;
         ProfScope ps(m, PDA_PROF_EVAL_TC, st);
-        const int rc = launch_recommend_tc(blk, m->tc_buf, plan, st);
+        const int rc = launch_recommend_tc(blk, m->tc_buf, plan, m0 == 0, st);
         if (rc) return fail(PDA_ERR_CUDA, "tensor-core eval launch failed (stage %d): %s", rc, cudaGetErrorString(cudaGetLastError()));
     }
     return PDA_OK;

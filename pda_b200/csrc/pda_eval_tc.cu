@@ -54,8 +54,9 @@ namespace tc {
 
 constexpr int TM = 128, TN = 128, KB = 64;          // UMMA tile, K block (64 bf16 = one 128 B swizzle row)
 constexpr int KX = 16;                              // extra K block (one UMMA K step), 32 B rows, 32B swizzle
-constexpr int MR = 4;                               // user tiles resident per CTA: every B tile from L2 serves MR * 128 users
-constexpr int ACC = 4;                              // TMEM accumulator ring: ACC * TN = 512 columns
+constexpr int MR_MAX = 4;                           // user tiles resident per CTA (template parameter MR = 3 or 4): every B tile
+                                                    // from L2 serves MR * 128 users; user tile mr owns TMEM accumulator mr
+constexpr int TMEM_COLS = 512;                      // MR * TN <= 512 accumulator columns
 constexpr int EPI_G = 2;                            // epilogue warp groups: each owns TN / EPI_G columns of every tile
 constexpr int EPI_COLS = TN / EPI_G;                // 64 columns per thread and tile = two tcgen05.ld x32
 constexpr int EPI_WARPS = 4 * EPI_G;                // warps 0-7: epilogue (TMEM lane quadrant = warp % 4, column half = warp / 4)
@@ -169,46 +170,60 @@ constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TN >
 // one warp per row: fp32 row (times scale[r]) -> bf16 row + L2 norm of the scaled row (rounded up) + the row's 16-column
 // extra block: xone ? (1, 1, 1, 0...) : the three bf16 pieces of xcol[r].  Rows >= n_rows are zero padding.
 // src_rows == nullptr: row r of src; else row src_rows[r] (gather of the eval users).
+constexpr int CONV_RPW = 4;      // rows per warp: all their loads are issued before the first use
 __global__ void __launch_bounds__(256) tc_convert_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ src_rows,
                                                               int64_t n_rows, int64_t n_pad, int d,
                                                               const float* __restrict__ scale, const float* __restrict__ xcol, int xone,
                                                               __nv_bfloat16* __restrict__ dst, __nv_bfloat16* __restrict__ dstx,
                                                               float* __restrict__ norm, int32_t* __restrict__ neg_flag) {
     const int lane = threadIdx.x & 31;
-    const int64_t r = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    if (r >= n_pad) return;
-    const bool real = r < n_rows;
-    float sq = 0.f;
-    if (real) {
-        const float sc = scale ? __ldg(scale + r) : 1.0f;
-        if (scale && lane == 0 && !(sc >= 0.0f)) atomicOr(neg_flag, 1);      // the bounds assume pop >= 0
-        const float* s = src + (src_rows ? (int64_t)src_rows[r] : r) * d;
-        for (int k = lane * 2; k < d; k += 64) {
-            const float2 v = *reinterpret_cast<const float2*>(s + k);
-            const float x = fmul(v.x, sc), y = fmul(v.y, sc);
-            sq = fmaf(x, x, fmaf(y, y, sq));
-            *reinterpret_cast<__nv_bfloat162*>(dst + r * d + k) = __floats2bfloat162_rn(x, y);
+    const int64_t r0 = ((blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5) * CONV_RPW;
+    if (r0 >= n_pad) return;
+    const int k = lane * 4;                      // d <= 128: one float4 per lane covers the row
+    float4 v[CONV_RPW];
+    float sc[CONV_RPW], xc[CONV_RPW];
+#pragma unroll
+    for (int i = 0; i < CONV_RPW; ++i) {
+        const int64_t r = r0 + i;
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sc[i] = 1.0f; xc[i] = 0.f;
+        if (r < n_rows) {
+            if (scale) sc[i] = __ldg(scale + r);
+            if (xcol) xc[i] = __ldg(xcol + r);
+            if (k < d) v[i] = ldg_f4(src + (src_rows ? (int64_t)src_rows[r] : r) * d + k);
         }
-    } else {
-        for (int k = lane * 2; k < d; k += 64) *reinterpret_cast<__nv_bfloat162*>(dst + r * d + k) = __floats2bfloat162_rn(0.f, 0.f);
     }
 #pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
-    if (lane == 0) norm[r] = sqrtf(sq) * 1.00001f;
-    if (dstx && lane < 8) {
-        float e0 = 0.f, e1 = 0.f;
-        if (real && lane < 2) {
-            if (xone) { e0 = 1.0f; e1 = lane == 0 ? 1.0f : 0.0f; }
-            else if (xcol) {
-                const float x = __ldg(xcol + r);
-                const float hi = __bfloat162float(__float2bfloat16_rn(x));
-                const float r1 = fsub(x, hi);                                // exact
-                const float mid = __bfloat162float(__float2bfloat16_rn(r1));
-                const float lo = __bfloat162float(__float2bfloat16_rn(fsub(r1, mid)));
-                if (lane == 0) { e0 = hi; e1 = mid; } else { e0 = lo; }
-            }
+    for (int i = 0; i < CONV_RPW; ++i) {
+        const int64_t r = r0 + i;
+        if (r >= n_pad) break;
+        const bool real = r < n_rows;
+        if (scale && real && lane == 0 && !(sc[i] >= 0.0f)) atomicOr(neg_flag, 1);      // the bounds assume pop >= 0
+        const float x = fmul(v[i].x, sc[i]), y = fmul(v[i].y, sc[i]), z = fmul(v[i].z, sc[i]), w = fmul(v[i].w, sc[i]);
+        float sq = fmaf(x, x, fmaf(y, y, fmaf(z, z, w * w)));
+        if (k < d) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(x, y), hi = __floats2bfloat162_rn(z, w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<const uint32_t*>(&lo); pk.y = *reinterpret_cast<const uint32_t*>(&hi);
+            *reinterpret_cast<uint2*>(dst + r * d + k) = pk;
         }
-        *reinterpret_cast<__nv_bfloat162*>(dstx + r * tc::KX + lane * 2) = __floats2bfloat162_rn(e0, e1);
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, off);
+        if (lane == 0) norm[r] = sqrtf(sq) * 1.00001f;
+        if (dstx && lane < 8) {
+            float e0 = 0.f, e1 = 0.f;
+            if (real && lane < 2) {
+                if (xone) { e0 = 1.0f; e1 = lane == 0 ? 1.0f : 0.0f; }
+                else if (xcol) {
+                    const float hi = __bfloat162float(__float2bfloat16_rn(xc[i]));
+                    const float r1 = fsub(xc[i], hi);                            // exact
+                    const float mid = __bfloat162float(__float2bfloat16_rn(r1));
+                    const float lo = __bfloat162float(__float2bfloat16_rn(fsub(r1, mid)));
+                    if (lane == 0) { e0 = hi; e1 = mid; } else { e0 = lo; }
+                }
+            }
+            *reinterpret_cast<__nv_bfloat162*>(dstx + r * tc::KX + lane * 2) = __floats2bfloat162_rn(e0, e1);
+        }
     }
 }
 
@@ -329,14 +344,15 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float thr, i
 
 }  // namespace tc
 
-template <int PASS, int KBLK, int KXT>      // KBLK = d / 64 K blocks, KXT = 1: the 16-column extra K block is present
+template <int PASS, int KBLK, int KXT, int MR>      // KBLK = d / 64 K blocks, KXT = 1: the 16-column extra K block is present
 __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmAx,
                                                               const __grid_constant__ CUtensorMap tmBx, SweepArgs a,
                                                               int n_stages) {
     using namespace tc;
-    static_assert(MR == ACC, "accumulator index = resident user tile index");
+    static_assert(MR >= 1 && MR <= MR_MAX && MR * TN <= TMEM_COLS, "accumulator index = resident user tile index");
+    constexpr int ACC = MR;
     extern __shared__ unsigned char smem_raw[];
     // 1024 B alignment for the 128B-swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -367,7 +383,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
         mbar_init(bar_afull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), ACC * TN);
+    if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
     fence_before();
     __syncthreads();
     fence_after();
@@ -518,7 +534,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
     }
     fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) { __syncwarp(); fence_after(); tmem_dealloc(tmem_base, ACC * TN); }
+    if (warp == MMA_WARP) { __syncwarp(); fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -588,21 +604,31 @@ __device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t* keys, int n
 }
 
 // one warp per row, n_c keys + 256 histogram bins per warp in dynamic shared memory
-__global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restrict__ cmax, int n_c, int64_t M, int64_t M_pad,
+__global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restrict__ cmax, int n_c, int n_valid, int64_t M, int64_t M_pad,
                                                             int se, int cw, const int32_t* __restrict__ users,
                                                             const int64_t* __restrict__ mask_indptr,
                                                             const int32_t* __restrict__ mask_items, int K,
                                                             const int32_t* __restrict__ neg_flag, float* __restrict__ tau) {
-    extern __shared__ uint32_t tau_keys[];
+    extern __shared__ __align__(16) uint32_t tau_keys[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t row = (int64_t)blockIdx.x * 4 + w;
     if (row >= M_pad) return;
     if (row >= M || *neg_flag) { if (lane == 0) tau[row] = INFINITY; return; }    // negative pop: no filter, exact kernel
-    uint32_t* kk = tau_keys + (size_t)w * (n_c + 256);
+    uint32_t* kk = tau_keys + (size_t)w * (n_c + 384);       // n_c (the row stride) is a multiple of 4; n_valid <= n_c keys exist
     int* hist = reinterpret_cast<int*>(kk + n_c);
-    for (int c = lane; c < n_c; c += 32) {
-        const float v = cmax[row * n_c + c];
-        kk[c] = v > -INFINITY ? f2key(v) : 0u;    // 0 sorts below every real value
+    const int n4 = n_c >> 2;
+    {
+        const float4* src = reinterpret_cast<const float4*>(cmax + row * n_c);
+#pragma unroll 4
+        for (int c4 = lane; c4 < n4; c4 += 32) {
+            const float4 v = __ldg(src + c4);
+            uint4 k;                                  // 0 sorts below every real value
+            k.x = (4 * c4 + 0 < n_valid && v.x > -INFINITY) ? f2key(v.x) : 0u;
+            k.y = (4 * c4 + 1 < n_valid && v.y > -INFINITY) ? f2key(v.y) : 0u;
+            k.z = (4 * c4 + 2 < n_valid && v.z > -INFINITY) ? f2key(v.z) : 0u;
+            k.w = (4 * c4 + 3 < n_valid && v.w > -INFINITY) ? f2key(v.w) : 0u;
+            reinterpret_cast<uint4*>(kk)[c4] = k;
+        }
     }
     __syncwarp();
     // A sampled chunk that holds ANY train item of this user is dropped: its maximum may belong to a masked item.
@@ -616,13 +642,21 @@ __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restr
             const int tile = it / tc::TN;
             if (tile % se == 0) {
                 const int c = (tile / se) * cpt + (it % tc::TN) / cw;
-                if (c < n_c) kk[c] = 0u;
+                if (c < n_valid) kk[c] = 0u;
             }
         }
         __syncwarp();
     }
+    // Pre-filter: the keys are dealt to 128 groups (4 per lane); the K-th largest of the 128 group maxima is a lower
+    // bound of the K-th largest key, and only ~1.5 % of the keys reach it.  The exact K-th largest is then selected
+    // among those survivors (the radix select over all n_c keys cost 4 passes of conflicting shared-memory atomics).
     int n_clean = 0;
-    for (int c = lane; c < n_c; c += 32) n_clean += kk[c] != 0u;
+    uint32_t g[4] = {0u, 0u, 0u, 0u};
+    for (int c4 = lane; c4 < n4; c4 += 32) {
+        const uint4 k = reinterpret_cast<const uint4*>(kk)[c4];
+        n_clean += (k.x != 0u) + (k.y != 0u) + (k.z != 0u) + (k.w != 0u);
+        g[0] = max(g[0], k.x); g[1] = max(g[1], k.y); g[2] = max(g[2], k.z); g[3] = max(g[3], k.w);
+    }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) n_clean += __shfl_xor_sync(0xffffffffu, n_clean, off);
     if (n_clean < K) {
@@ -630,14 +664,48 @@ __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restr
         return;
     }
     int above;
-    const uint32_t kth = warp_kth_largest(kk, n_c, K, hist, lane, &above);
+    uint32_t* gk = reinterpret_cast<uint32_t*>(hist) + 256;      // 128 group maxima behind the histogram
+#pragma unroll
+    for (int q = 0; q < 4; ++q) gk[q * 32 + lane] = g[q];
+    __syncwarp();
+    int n_sel = n_c;
+    int n_groups = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) n_groups += g[q] != 0u;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) n_groups += __shfl_xor_sync(0xffffffffu, n_groups, off);
+    if (n_groups >= K) {
+        const uint32_t l0 = warp_kth_largest(gk, 128, K, hist, lane, &above);
+        int ns = 0;
+        for (int c0 = 0; c0 < n4; c0 += 32) {
+            const int c4 = c0 + lane;
+            const uint4 k4 = c4 < n4 ? reinterpret_cast<const uint4*>(kk)[c4] : make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t kv[4] = {k4.x, k4.y, k4.z, k4.w};
+            __syncwarp();                                              // in place: everything of this round is in registers
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const bool keep = kv[q] >= l0 && kv[q] != 0u;
+                const unsigned bal = __ballot_sync(0xffffffffu, keep);
+                if (keep) kk[ns + __popc(bal & ((1u << lane) - 1u))] = kv[q];      // ns + rank <= elements read so far
+                ns += __popc(bal);
+            }
+        }
+        __syncwarp();
+        n_sel = ns;
+    }
+    const uint32_t kth = warp_kth_largest(kk, n_sel, K, hist, lane, &above);
     float t = key2f(kth);
     t = t - fabsf(t) * 1e-5f - 1e-30f;
     if (lane == 0) tau[row] = t;
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// exact rescoring + top-K + certificate: one warp per row
+// exact rescoring + top-K + certificate, three kernels so that every phase runs at its own occupancy:
+//   collect  one warp per row: candidate segments (+ the pop-branch items) -> compact, mask-free id list in HBM and
+//            one work item per round of 32 candidates
+//   score    persistent warps over the work items: 32 item rows staged with cp.async (each row one coalesced request,
+//            all in flight together), then lane l runs the sequential-k chain of candidate l out of shared memory
+//   select   one warp per row: certificate, K-th largest exact score by radix select, bitonic sort, output
 // ------------------------------------------------------------------------------------------------------------
 struct RescoreArgs {
     const float* U; const float* I; int64_t M; int64_t N;
@@ -648,26 +716,26 @@ struct RescoreArgs {
     int tiles_per_split;
     const float* tau;
     int K;
-    int rc;             // per-row capacity of the compacted candidate list in shared memory
+    int rc;             // per-row capacity of the compacted candidate list (multiple of 32, <= 2048)
     // mode 1, the pop branch of the upper bound: per 128-item tile the largest pop, its item, the second largest
     const float* tile_col; const int32_t* tile_arg; const float* tile_col2; int n_tiles;
+    int32_t* clist;     // [M][rc] unmasked candidate ids of the row
+    uint32_t* ckeys;    // [M][rc] order-preserving keys of their exact transformed scores
+    int32_t* ccount;    // [M] entries of clist, -1 = the row cannot be certified (overflow)
+    int32_t* work;      // work items of the score kernel: row << 6 | round
+    int32_t* n_work;
     int32_t* ids_out; float* scores_out;
     int32_t* flag;      // [M] 1 = not certified
 };
 
 constexpr int SORT_MAX = 256;
-constexpr int HOT_CAP = 2 * SORT_MAX;       // hot-tile list of a row (lives in the sort buffer, which is used later)
+constexpr int HOT_CAP = 512;                // hot-tile list of a row
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
-}
-
-// per-warp shared memory of the rescoring kernel
-__host__ __device__ inline size_t rescore_warp_bytes(int D, int RC, int n_seg) {
-    return (size_t)33 * (D + 4) * 4 + (size_t)RC * 8 + (size_t)((n_seg + 4) / 4 * 4) * 4;
 }
 
 // is item j among the sweep's candidates of this row?  (segment sg of the compact list, ascending ids)
@@ -681,38 +749,24 @@ __device__ __forceinline__ bool in_segment(const int* cid, const int* soff, int 
     return l < send && cid[l] == j;
 }
 
+__host__ __device__ inline size_t collect_warp_bytes(int RC, int n_seg) {
+    return (size_t)RC * 4 + (size_t)HOT_CAP * 4 + (size_t)((n_seg + 4) / 4 * 4) * 4;
+}
+
 //  1. the row's candidate segments -> one compact id list in shared memory (+ the pop-branch items, mode 1)
 //  2. train items out: every masked item lives in exactly one segment (ascending ids) -> binary search there
-//  3. exact fp32 score (the sequential-k spec) + transform of every remaining candidate: item rows are staged 32 at a
-//     time with cp.async (every row one coalesced request, all in flight together), then lane l runs the sequential
-//     chain of candidate l out of shared memory
-//  4. K-th largest exact score by radix select, survivors (>= it) bitonic-sorted by (score desc, id asc)
-//  5. certificate: no overflow and >= K unmasked candidates with exact score >= tau
-template <int D>
-__global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
+//  3. the surviving ids -> clist, one work item per 32 of them
+__global__ void __launch_bounds__(128) tc_collect_kernel(RescoreArgs a) {
     extern __shared__ __align__(16) unsigned char rs_smem[];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int RC = a.rc;
-    constexpr int S = D + 4;                // staged row stride in floats: (S / 4) odd -> conflict-free 128-bit reads
-    // per warp: stage[32][S] + us[S] | cid[RC] | ckey[RC] | soff[n_seg + 1]; the sort buffer (= hot-tile list of step
-    // 1b) and the histogram alias the first 3 KB of the stage: they are used before / after step 3 only
-    static_assert(32 * S * 4 >= SORT_MAX * 8 + 1024, "sort buffer + histogram must fit below the user row");
-    const size_t per_warp = rescore_warp_bytes(D, RC, a.n_seg);
-    unsigned char* base = rs_smem + (size_t)w * per_warp;
-    float* stage = reinterpret_cast<float*>(base);
-    float* us = stage + 32 * S;
-    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(base);
-    int* hist = reinterpret_cast<int*>(base + (size_t)SORT_MAX * 8);
-    unsigned char* b2 = base + (size_t)33 * S * 4;
-    int* cid = reinterpret_cast<int*>(b2);
-    uint32_t* ckey = reinterpret_cast<uint32_t*>(b2 + (size_t)RC * 4);
-    int* soff = reinterpret_cast<int*>(b2 + (size_t)RC * 8);
+    unsigned char* base = rs_smem + (size_t)w * collect_warp_bytes(RC, a.n_seg);
+    int* cid = reinterpret_cast<int*>(base);
+    int* hot = cid + RC;
+    int* soff = hot + HOT_CAP;
     const int64_t row = (int64_t)blockIdx.x * 4 + w;
     if (row >= a.M) return;
-    const int K = a.K;
     const int u = a.users[row];
-    const float* ur = a.U + (int64_t)u * D;
-    if (lane < D / 4) cp_async16(us + 4 * lane, ur + 4 * lane);       // the user row: read by every lane (broadcast)
 
     // 1. compact
     bool overflow = false;
@@ -733,11 +787,15 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
     overflow = __any_sync(0xffffffffu, overflow) || tot > RC;
     if (lane == 0) soff[a.n_seg] = tot;
     __syncwarp();
-    if (overflow) { if (lane == 0) a.flag[row] = 1; cp_async_wait_all(); return; }
-    for (int sg = 0; sg < a.n_seg; ++sg) {
-        const int o = soff[sg], nn = soff[sg + 1] - o;
-        const int32_t* cl = a.cand + (row * a.n_seg + sg) * a.seg_cap;
-        for (int c = lane; c < nn; c += 32) cid[o + c] = cl[c];
+    if (overflow) { if (lane == 0) a.ccount[row] = -1; return; }
+    // all segments at once: element c of the compact list lives in the segment found by bisection of soff
+    for (int c = lane; c < tot; c += 32) {
+        int lo = 0, hi = a.n_seg;                       // largest sg with soff[sg] <= c
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (soff[mid] <= c) lo = mid; else hi = mid;
+        }
+        cid[c] = a.cand[(row * a.n_seg + lo) * a.seg_cap + (c - soff[lo])];
     }
     __syncwarp();
 
@@ -746,10 +804,8 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
     //     listed first (none at all once tau > max pop, the fitted-model case); a tile with a single such item (its
     //     second largest pop is below tau) is settled by one lane, the others are scanned by the warp.
     int n_extra = 0;
-    const float tau = a.tau[row];
     if (a.mode == 1) {
-        const float tl = tc::tau_lower(tau);
-        int* hot = reinterpret_cast<int*>(sortbuf);
+        const float tl = tc::tau_lower(a.tau[row]);
         int n_hot = 0;
         for (int tb = 0; tb < a.n_tiles; tb += 128) {
             bool h[4];
@@ -765,7 +821,7 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
                 n_hot += __popc(bal);
             }
         }
-        if (n_hot > HOT_CAP) { if (lane == 0) a.flag[row] = 1; cp_async_wait_all(); return; }
+        if (n_hot > HOT_CAP) { if (lane == 0) a.ccount[row] = -1; return; }
         __syncwarp();
         for (int i0 = 0; i0 < n_hot && tot + n_extra <= RC; i0 += 32) {
             const int i = i0 + lane;
@@ -804,7 +860,7 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
                 }
             }
         }
-        if (tot + n_extra > RC) { if (lane == 0) a.flag[row] = 1; cp_async_wait_all(); return; }
+        if (tot + n_extra > RC) { if (lane == 0) a.ccount[row] = -1; return; }
         __syncwarp();
     }
 
@@ -829,29 +885,56 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
     }
     tot += n_extra;
 
-    // 3. exact scores, 32 candidates per round
-    int n_cert = 0;
-    cp_async_wait_all();
+    // 3. unmasked ids -> HBM, work items
+    int nw = 0;
+    int32_t* out = a.clist + row * RC;
     for (int c0 = 0; c0 < tot; c0 += 32) {
-        const int nb = min(32, tot - c0);
+        const int c = c0 + lane;
+        const int j = c < tot ? cid[c] : -1;
+        const unsigned bal = __ballot_sync(0xffffffffu, j >= 0);
+        if (j >= 0) out[nw + __popc(bal & ((1u << lane) - 1u))] = j;
+        nw += __popc(bal);
+    }
+    const int nr = (nw + 31) >> 5;
+    int wbase = 0;
+    if (lane == 0) { a.ccount[row] = nw; if (nr) wbase = atomicAdd(a.n_work, nr); }
+    wbase = __shfl_sync(0xffffffffu, wbase, 0);
+    for (int r = lane; r < nr; r += 32) a.work[wbase + r] = (int32_t)(row << 6) | r;
+}
+
+// exact fp32 score (the sequential-k spec) + transform of 32 candidates per work item
+template <int D>
+__global__ void __launch_bounds__(128) tc_score_kernel(RescoreArgs a) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int S = D + 4;                // staged row stride in floats: (S / 4) odd -> conflict-free 128-bit reads
+    float* stage = reinterpret_cast<float*>(rs_smem) + (size_t)w * 33 * S;
+    float* us = stage + 32 * S;
+    const int total = *a.n_work;
+    for (int wi = blockIdx.x * 4 + w; wi < total; wi += gridDim.x * 4) {
+        const int item = a.work[wi];
+        const int64_t row = item >> 6;
+        const int c0 = (item & 63) * 32;
+        const int nb = min(32, a.ccount[row] - c0);
+        const int32_t* cl = a.clist + row * a.rc + c0;
+        const float* ur = a.U + (int64_t)a.users[row] * D;
+        if (lane < D / 4) cp_async16(us + 4 * lane, ur + 4 * lane);       // the user row: read by every lane (broadcast)
+        const int myj = lane < nb ? cl[lane] : 0;
         if (D == 128) {
             for (int r = 0; r < nb; ++r) {
-                const int j = cid[c0 + r];
-                if (j >= 0) cp_async16(stage + r * S + 4 * lane, a.I + (int64_t)j * D + 4 * lane);
+                const int j = __shfl_sync(0xffffffffu, myj, r);
+                cp_async16(stage + r * S + 4 * lane, a.I + (int64_t)j * D + 4 * lane);
             }
         } else {
             for (int r = 0; r < nb; r += 2) {
-                const int rr = r + (lane >> 4);
-                const int j = rr < nb ? cid[c0 + rr] : -1;
-                if (j >= 0) cp_async16(stage + rr * S + 4 * (lane & 15), a.I + (int64_t)j * D + 4 * (lane & 15));
+                const int rr = min(r + (lane >> 4), nb - 1);              // odd nb: the last row is copied twice
+                const int j = __shfl_sync(0xffffffffu, myj, rr);
+                cp_async16(stage + rr * S + 4 * (lane & 15), a.I + (int64_t)j * D + 4 * (lane & 15));
             }
         }
         cp_async_wait_all();
         __syncwarp();
-        const int c = c0 + lane;
-        const int j = c < tot ? cid[c] : -1;
-        uint32_t key = 0;
-        if (j >= 0) {
+        if (lane < nb) {
             const float* ir = stage + lane * S;
             float acc = 0.0f;
 #pragma unroll 8
@@ -862,14 +945,37 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
                 acc = fadd(acc, fmul(uv.z, iv.z)); acc = fadd(acc, fmul(uv.w, iv.w));
             }
             float y;
-            if (a.mode == 1) y = fmul(elu_p1(acc), __ldg(a.pop + j));
-            else y = a.col_bias ? fadd(acc, __ldg(a.col_bias + j)) : acc;
-            key = f2key(y);
-            if (key == 0u) key = 1u;          // (only -NaN patterns map to 0) keep 0 for "not a candidate"
-            n_cert += y >= tau;
+            if (a.mode == 1) y = fmul(elu_p1(acc), __ldg(a.pop + myj));
+            else y = a.col_bias ? fadd(acc, __ldg(a.col_bias + myj)) : acc;
+            uint32_t key = f2key(y);
+            if (key == 0u) key = 1u;          // (only -NaN patterns map to 0) 0 stays below every candidate
+            a.ckeys[row * a.rc + c0 + lane] = key;
         }
-        if (c < tot) ckey[c] = key;
-        __syncwarp();                          // the stage is rewritten by the next round
+        __syncwarp();                          // the stage is rewritten by the next work item
+    }
+}
+
+//  4. certificate: >= K unmasked candidates with exact score >= tau
+//  5. K-th largest exact score by radix select, survivors (>= it) bitonic-sorted by (score desc, id asc)
+__global__ void __launch_bounds__(128) tc_select_kernel(RescoreArgs a) {
+    extern __shared__ __align__(16) unsigned char rs_smem[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int RC = a.rc;
+    unsigned char* base = rs_smem + (size_t)w * ((size_t)SORT_MAX * 8 + 1024 + (size_t)RC * 4);
+    unsigned long long* sortbuf = reinterpret_cast<unsigned long long*>(base);
+    int* hist = reinterpret_cast<int*>(base + (size_t)SORT_MAX * 8);
+    uint32_t* ckey = reinterpret_cast<uint32_t*>(base + (size_t)SORT_MAX * 8 + 1024);
+    const int64_t row = (int64_t)blockIdx.x * 4 + w;
+    if (row >= a.M) return;
+    const int K = a.K;
+    const int tot = a.ccount[row];
+    if (tot < K) { if (lane == 0) a.flag[row] = 1; return; }       // overflow (-1) or too few candidates
+    const float tau = a.tau[row];
+    int n_cert = 0;
+    for (int c = lane; c < tot; c += 32) {
+        const uint32_t k = a.ckeys[row * RC + c];
+        ckey[c] = k;
+        n_cert += key2f(k) >= tau;
     }
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) n_cert += __shfl_xor_sync(0xffffffffu, n_cert, off);
@@ -886,7 +992,7 @@ __global__ void __launch_bounds__(128) tc_rescore_kernel(RescoreArgs a) {
         const unsigned bal = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int pos = ns + __popc(bal & ((1u << lane) - 1u));
-            if (pos < SORT_MAX) sortbuf[pos] = ((unsigned long long)ckey[c] << 32) | (uint32_t)(0x7fffffff - cid[c]);
+            if (pos < SORT_MAX) sortbuf[pos] = ((unsigned long long)ckey[c] << 32) | (uint32_t)(0x7fffffff - a.clist[row * RC + c]);
         }
         ns += __popc(bal);
     }
@@ -974,6 +1080,10 @@ static int env_int(const char* name, int dflt) {
 size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     using namespace tc;
     static_assert(TM == TN, "one tensor-map box shape serves both operands");
+    // user tiles per CTA: 3 leaves room for a third B stage at d = 128 (the TMA round trip then hides behind two tiles
+    // of MMAs), 4 reads every B tile from L2 for 512 instead of 384 users
+    p->mr = env_int("PDA_TC_MR", a.d == 128 ? 3 : 4) == 3 ? 3 : 4;
+    const int MR = p->mr;
     p->M_pad = (a.M + TM * MR - 1) / (TM * MR) * (TM * MR);
     p->N_pad = (a.N + TN - 1) / TN * TN;
     p->n_tiles = (int)(p->N_pad / TN);
@@ -988,7 +1098,8 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
         if (want > se) se = want;
     }
     p->cw = cw; p->se = se;
-    p->n_c = (p->n_tiles + se - 1) / se * (TN / cw);
+    p->n_valid = (p->n_tiles + se - 1) / se * (TN / cw);
+    p->n_c = (p->n_valid + 3) / 4 * 4;                        // row stride of cmax: float4 loads in the selection kernel
     // item-range splits: enough CTAs to fill the GPU in whole waves (one CTA per SM: shared memory), equal lengths
     const int m_tiles = (int)(p->M_pad / (TM * MR));
     const int n_sm = 148;
@@ -1017,16 +1128,19 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     // compacted list a rescoring warp holds in shared memory: ~K * (1 + se) * 1.6 entries expected
     p->rc = p->se <= 2 ? 512 : (p->se <= 6 ? 1024 : 2048);
     size_t o = 0;
+    // item side first: these offsets depend on (N, d) only, so the item operands prepared for the first user block of a
+    // call stay valid for the following blocks
     p->o_Ib = o; o += al256((size_t)p->N_pad * a.d * 2);
-    p->o_Ub = o; o += al256((size_t)p->M_pad * a.d * 2);
     p->o_Ix = o; o += al256((size_t)p->N_pad * KX * 2);
-    p->o_Ux = o; o += al256((size_t)p->M_pad * KX * 2);
     p->o_inorm = o; o += al256((size_t)p->N_pad * 4);
-    p->o_unorm = o; o += al256((size_t)p->M_pad * 4);
     p->o_tnorm = o; o += al256((size_t)p->n_tiles * 4);
     p->o_tcolmax = o; o += al256((size_t)p->n_tiles * 4);
     p->o_targ = o; o += al256((size_t)p->n_tiles * 4);
     p->o_tcol2 = o; o += al256((size_t)p->n_tiles * 4);
+    p->o_nflag = o; o += 256;          // [0] rows without a certificate, [1] negative-pop flag
+    p->o_Ub = o; o += al256((size_t)p->M_pad * a.d * 2);
+    p->o_Ux = o; o += al256((size_t)p->M_pad * KX * 2);
+    p->o_unorm = o; o += al256((size_t)p->M_pad * 4);
     p->o_cmax = o; o += al256((size_t)p->n_c * p->M_pad * 4);
     p->o_tau = o; o += al256((size_t)p->M_pad * 4);
     p->o_cnt = o; o += al256((size_t)p->M_pad * p->n_seg * 4);
@@ -1034,13 +1148,17 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->o_flag = o; o += al256((size_t)p->M_pad * 4);
     p->o_frows = o; o += al256((size_t)p->M_pad * 4);
     p->o_fusers = o; o += al256((size_t)p->M_pad * 4);
-    p->o_nflag = o; o += 256;          // [0] rows without a certificate, [1] negative-pop flag
+    p->o_clist = o; o += al256((size_t)p->M_pad * p->rc * 4);
+    p->o_ckeys = o; o += al256((size_t)p->M_pad * p->rc * 4);
+    p->o_ccount = o; o += al256((size_t)p->M_pad * 4);
+    p->o_work = o; o += al256((size_t)p->M_pad * (p->rc / 32) * 4);
+    p->o_nwork = o; o += 256;
     return o;
 }
 
 struct SweepMaps { CUtensorMap A, B, Ax, Bx; };
 
-template <int PASS, int KBLK, int KXT>
+template <int PASS, int KBLK, int KXT, int MR>
 static int launch_sweep_t(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p, int m_tiles, cudaStream_t st) {
     using namespace tc;
     const int kblocks = s.d / KB;
@@ -1051,21 +1169,25 @@ static int launch_sweep_t(const SweepMaps& tm, const SweepArgs& s, const TcPlan&
     if (n_stages > 6) n_stages = 6;
     if (n_stages < 2) return 1;
     const size_t smem = fixed + a_bytes + (size_t)n_stages * b_bytes;
-    if (cudaFuncSetAttribute(tc_sweep_kernel<PASS, KBLK, KXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_sweep_kernel<PASS, KBLK, KXT, MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return 2;
     dim3 grid(m_tiles, p.splits);
-    tc_sweep_kernel<PASS, KBLK, KXT><<<grid, NT, smem, st>>>(tm.A, tm.B, tm.Ax, tm.Bx, s, n_stages);
+    tc_sweep_kernel<PASS, KBLK, KXT, MR><<<grid, NT, smem, st>>>(tm.A, tm.B, tm.Ax, tm.Bx, s, n_stages);
     return 0;
 }
 
 template <int PASS>
 static int launch_sweep(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p, int m_tiles, cudaStream_t st) {
-    if (s.d == 64) return s.kx ? launch_sweep_t<PASS, 1, 1>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 1, 0>(tm, s, p, m_tiles, st);
-    return s.kx ? launch_sweep_t<PASS, 2, 1>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 2, 0>(tm, s, p, m_tiles, st);
+    if (p.mr == 3) {
+        if (s.d == 64) return s.kx ? launch_sweep_t<PASS, 1, 1, 3>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 1, 0, 3>(tm, s, p, m_tiles, st);
+        return s.kx ? launch_sweep_t<PASS, 2, 1, 3>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 2, 0, 3>(tm, s, p, m_tiles, st);
+    }
+    if (s.d == 64) return s.kx ? launch_sweep_t<PASS, 1, 1, 4>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 1, 0, 4>(tm, s, p, m_tiles, st);
+    return s.kx ? launch_sweep_t<PASS, 2, 1, 4>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 2, 0, 4>(tm, s, p, m_tiles, st);
 }
 
 // prep shared by the filter pipeline and the diagnostics entry: bf16 operands, norms, tile maxima, tensor maps
-static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm, SweepArgs* s, cudaStream_t st) {
+static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm, SweepArgs* s, bool prep_items, cudaStream_t st) {
     using namespace tc;
     __nv_bfloat16* Ib = (__nv_bfloat16*)(b + p.o_Ib);
     __nv_bfloat16* Ub = (__nv_bfloat16*)(b + p.o_Ub);
@@ -1077,19 +1199,21 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
     // the column term folded into the GEMM: pop ("condition": it also scales the item rows) or the column bias
     const float* xcol = a.mode == 1 ? a.pop : a.col_bias;
     const int kx = xcol ? 1 : 0;
-    cudaMemsetAsync(nflag, 0, 8, st);
-    tc_convert_rows_kernel<<<(unsigned)((p.N_pad * 32 + 255) / 256), 256, 0, st>>>(a.I, nullptr, a.N, p.N_pad, a.d,
-                                                                                  a.mode == 1 ? a.pop : nullptr, xcol, 0, Ib,
-                                                                                  kx ? Ix : nullptr, inorm, nflag + 1);
-    tc_convert_rows_kernel<<<(unsigned)((p.M_pad * 32 + 255) / 256), 256, 0, st>>>(a.U, a.users, a.M, p.M_pad, a.d, nullptr, nullptr, 1,
+    cudaMemsetAsync(nflag, 0, prep_items ? 8 : 4, st);
+    if (prep_items) {
+        tc_convert_rows_kernel<<<(unsigned)((p.N_pad / CONV_RPW * 32 + 255) / 256), 256, 0, st>>>(a.I, nullptr, a.N, p.N_pad, a.d,
+                                                                                      a.mode == 1 ? a.pop : nullptr, xcol, 0, Ib,
+                                                                                      kx ? Ix : nullptr, inorm, nflag + 1);
+        tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(inorm, p.n_tiles, tnorm, p.N_pad);
+        if (a.mode == 1)
+            tc_tile_top2_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(xcol, p.n_tiles, a.N, tcolmax,
+                                                                                                 (int32_t*)(b + p.o_targ),
+                                                                                                 (float*)(b + p.o_tcol2));
+        else if (kx)
+            tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(xcol, p.n_tiles, tcolmax, a.N);
+    }
+    tc_convert_rows_kernel<<<(unsigned)((p.M_pad / CONV_RPW * 32 + 255) / 256), 256, 0, st>>>(a.U, a.users, a.M, p.M_pad, a.d, nullptr, nullptr, 1,
                                                                                   Ub, kx ? Ux : nullptr, unorm, nflag + 1);
-    tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(inorm, p.n_tiles, tnorm, p.N_pad);
-    if (a.mode == 1)
-        tc_tile_top2_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(xcol, p.n_tiles, a.N, tcolmax,
-                                                                                             (int32_t*)(b + p.o_targ),
-                                                                                             (float*)(b + p.o_tcol2));
-    else if (kx)
-        tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(xcol, p.n_tiles, tcolmax, a.N);
 
     if (make_map(&tm->A, Ub, p.M_pad, a.d, KB) || make_map(&tm->B, Ib, p.N_pad, a.d, KB)) return 3;
     if (kx) {
@@ -1110,26 +1234,28 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
 }
 
 // Runs the whole filter pipeline for one block of users (M <= what tc_scratch_bytes was sized for).
+// prep_items = false: the item operands in `scratch` were prepared by an earlier block of the same call (same tables,
+// pop, bias).
 // `scratch` = device buffer of tc_scratch_bytes(); results -> a.ids_out / a.scores_out.
-int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, cudaStream_t st) {
+int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, bool prep_items, cudaStream_t st) {
     using namespace tc;
     if (!tc_supported(a)) return 1;
     char* b = (char*)scratch;
     float* tau = (float*)(b + p.o_tau);
     int32_t* flag = (int32_t*)(b + p.o_flag); int32_t* frows = (int32_t*)(b + p.o_frows);
     int32_t* fusers = (int32_t*)(b + p.o_fusers); int32_t* nflag = (int32_t*)(b + p.o_nflag);
-    const int m_tiles = (int)(p.M_pad / (TM * MR));
+    const int m_tiles = (int)(p.M_pad / (TM * p.mr));
 
     SweepMaps tm;
     SweepArgs s;
-    int rc = tc_prepare(a, b, p, &tm, &s, st);
+    int rc = tc_prepare(a, b, p, &tm, &s, prep_items, st);
     if (rc) return rc;
 
     rc = launch_sweep<0>(tm, s, p, m_tiles, st);
     if (rc) return 10 + rc;
-    const size_t tau_smem = (size_t)4 * (p.n_c + 256) * 4;
+    const size_t tau_smem = (size_t)4 * (p.n_c + 384) * 4;
     if (cudaFuncSetAttribute(tc_tau_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tau_smem) != cudaSuccess) return 15;
-    tc_tau_select_kernel<<<(unsigned)((p.M_pad + 3) / 4), 128, tau_smem, st>>>(s.cmax, p.n_c, a.M, p.M_pad, p.se, p.cw, a.users,
+    tc_tau_select_kernel<<<(unsigned)((p.M_pad + 3) / 4), 128, tau_smem, st>>>(s.cmax, p.n_c, p.n_valid, a.M, p.M_pad, p.se, p.cw, a.users,
                                                                                a.mask_indptr, a.mask_items, a.K, nflag + 1, tau);
     rc = launch_sweep<1>(tm, s, p, m_tiles, st);
     if (rc) return 20 + rc;
@@ -1143,14 +1269,24 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, cudaS
     r.tile_col = s.tile_col; r.tile_arg = (const int32_t*)(b + p.o_targ); r.tile_col2 = (const float*)(b + p.o_tcol2);
     r.n_tiles = p.n_tiles;
     r.ids_out = a.ids_out; r.scores_out = a.scores_out; r.flag = flag;
-    const size_t rs_smem = 4 * rescore_warp_bytes(a.d, p.rc, p.n_seg);
+    r.clist = (int32_t*)(b + p.o_clist); r.ckeys = (uint32_t*)(b + p.o_ckeys); r.ccount = (int32_t*)(b + p.o_ccount);
+    r.work = (int32_t*)(b + p.o_work); r.n_work = (int32_t*)(b + p.o_nwork);
+    cudaMemsetAsync(r.n_work, 0, 4, st);
+    const size_t col_smem = 4 * collect_warp_bytes(p.rc, p.n_seg);
+    if (cudaFuncSetAttribute(tc_collect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)col_smem) != cudaSuccess) return 25;
+    tc_collect_kernel<<<(unsigned)((a.M + 3) / 4), 128, col_smem, st>>>(r);
+    const size_t sc_smem = (size_t)4 * 33 * (a.d + 4) * 4;
+    const int sc_blocks = 148 * (int)((227 * 1024) / (sc_smem + 1024));       // persistent: every SM full
     if (a.d == 64) {
-        cudaFuncSetAttribute(tc_rescore_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem);
-        tc_rescore_kernel<64><<<(unsigned)((a.M + 3) / 4), 128, rs_smem, st>>>(r);
+        cudaFuncSetAttribute(tc_score_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem);
+        tc_score_kernel<64><<<sc_blocks, 128, sc_smem, st>>>(r);
     } else {
-        cudaFuncSetAttribute(tc_rescore_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem);
-        tc_rescore_kernel<128><<<(unsigned)((a.M + 3) / 4), 128, rs_smem, st>>>(r);
+        cudaFuncSetAttribute(tc_score_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sc_smem);
+        tc_score_kernel<128><<<sc_blocks, 128, sc_smem, st>>>(r);
     }
+    const size_t sel_smem = (size_t)4 * ((size_t)SORT_MAX * 8 + 1024 + (size_t)p.rc * 4);
+    if (cudaFuncSetAttribute(tc_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem) != cudaSuccess) return 26;
+    tc_select_kernel<<<(unsigned)((a.M + 3) / 4), 128, sel_smem, st>>>(r);
     tc_compact_flags_kernel<<<148, 256, 0, st>>>(flag, a.M, a.users, frows, fusers, nflag);
 
     // rows without a certificate: the exact kernel, sized on the device (CTAs beyond ceil(n/64) exit at once)
@@ -1167,10 +1303,10 @@ int launch_tc_debug_dense(const EvalArgs& a, void* scratch, const TcPlan& p, flo
     if (!tc_supported(a)) return 1;
     SweepMaps tm;
     SweepArgs s;
-    int rc = tc_prepare(a, (char*)scratch, p, &tm, &s, st);
+    int rc = tc_prepare(a, (char*)scratch, p, &tm, &s, true, st);
     if (rc) return rc;
     s.dense = dense; s.dense_ld = p.N_pad;
-    rc = launch_sweep<2>(tm, s, p, (int)(p.M_pad / (TM * MR)), st);
+    rc = launch_sweep<2>(tm, s, p, (int)(p.M_pad / (TM * p.mr)), st);
     return rc ? 10 + rc : 0;
 }
 
