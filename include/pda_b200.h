@@ -120,7 +120,9 @@ int pda_adam_stats(pda_model* m, int64_t* out2, int reset);
 #define PDA_PROF_EVAL 3
 #define PDA_PROF_EVAL_TC 4
 #define PDA_PROF_ADAM_CATCHUP 5   /* lazy Adam: replay of skipped steps for the rows of the batch (+ flushes) */
-#define PDA_PROF_KINDS 6
+#define PDA_PROF_EVAL_SWEEP_A 6   /* tensor eval: the sampled tcgen05 sweep (lower bounds -> tau) */
+#define PDA_PROF_EVAL_SWEEP_B 7   /* tensor eval: the full tcgen05 sweep (candidates) -- the dominant eval kernel */
+#define PDA_PROF_KINDS 8
 int pda_profile_enable(pda_model* m, int on);
 int pda_profile_read(pda_model* m, double* ms_sum, int32_t* count);
 

@@ -878,7 +878,15 @@ static int do_recommend(pda_model* m, const EvalArgs& a, int backend, cudaStream
         tc_scratch_bytes(blk, &plan);
         m->tc_last_plan = plan; m->tc_last_M = blk.M;
         ProfScope ps(m, PDA_PROF_EVAL_TC, st);
-        const int rc = launch_recommend_tc(blk, m->tc_buf, plan, m0 == 0, st);
+        cudaEvent_t ev[4];
+        bool sub = false;
+        if (m->prof_on && m->prof_ev && m->prof_n[PDA_PROF_EVAL_SWEEP_A] < PDA_PROF_SLOTS && m->prof_n[PDA_PROF_EVAL_SWEEP_B] < PDA_PROF_SLOTS) {
+            const int sa = m->prof_n[PDA_PROF_EVAL_SWEEP_A]++, sb = m->prof_n[PDA_PROF_EVAL_SWEEP_B]++;
+            ev[0] = m->prof_ev[PDA_PROF_EVAL_SWEEP_A][sa][0]; ev[1] = m->prof_ev[PDA_PROF_EVAL_SWEEP_A][sa][1];
+            ev[2] = m->prof_ev[PDA_PROF_EVAL_SWEEP_B][sb][0]; ev[3] = m->prof_ev[PDA_PROF_EVAL_SWEEP_B][sb][1];
+            sub = true;
+        }
+        const int rc = launch_recommend_tc(blk, m->tc_buf, plan, m0 == 0, st, sub ? ev : nullptr);
         if (rc) return fail(PDA_ERR_CUDA, "tensor-core eval launch failed (stage %d): %s", rc, cudaGetErrorString(cudaGetLastError()));
     }
     return PDA_OK;

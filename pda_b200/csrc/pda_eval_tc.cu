@@ -144,6 +144,30 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_st64(uint32_t taddr, const uint32_t* v) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x64.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63, %64};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31]), "r"(v[32]), "r"(v[33]), "r"(v[34]), "r"(v[35]), "r"(v[36]), "r"(v[37]), "r"(v[38]), "r"(v[39]), "r"(v[40]), "r"(v[41]), "r"(v[42]), "r"(v[43]), "r"(v[44]), "r"(v[45]), "r"(v[46]), "r"(v[47]), "r"(v[48]), "r"(v[49]), "r"(v[50]), "r"(v[51]), "r"(v[52]), "r"(v[53]), "r"(v[54]), "r"(v[55]), "r"(v[56]), "r"(v[57]), "r"(v[58]), "r"(v[59]), "r"(v[60]), "r"(v[61]), "r"(v[62]), "r"(v[63]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// A operand from tensor memory (row r of the tile = TMEM lane r, two bf16 per 32-bit column), B from shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart (SBO), version 1, layout type 2.
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -277,6 +301,8 @@ struct SweepArgs {
     int tiles_per_split;       // each CTA of blockIdx.y sweeps [y * tiles_per_split, ...)
     int se;                    // pass A: every se-th tile is sampled
     float cAB, cB;             // E = cAB * |u| * max|w_j| + cB * max|x_j|  (maxima over the tile)
+    const __nv_bfloat16* Ub;   // [M_pad][d] bf16 user rows, [M_pad][16] extra block (TS mode reads them directly)
+    const __nv_bfloat16* Ux;
     const float* unorm;        // [M_pad]
     const float* tile_inorm;   // [n_tiles] max |w_j|
     const float* tile_col;     // [n_tiles] max |x_j| (nullptr when kx == 0)
@@ -288,6 +314,7 @@ struct SweepArgs {
                                // segment = (item split, column half): exactly one owner thread, no atomics
     int32_t* cnt;              // [M_pad][n_seg] entries written (> seg_cap = overflow)
     int n_seg, seg_cap;
+    int interleave;            // shared-memory form: interleave the MMAs of two user tiles
     // pass 2 (diagnostics): the raw accumulators
     float* dense; int64_t dense_ld;
 };
@@ -344,20 +371,26 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float thr, i
 
 }  // namespace tc
 
-template <int PASS, int KBLK, int KXT, int MR>      // KBLK = d / 64 K blocks, KXT = 1: the 16-column extra K block is present
+// KBLK = d / 64 K blocks; KXT = 1: the 16-column extra K block is present; MR user tiles per CTA;
+// TS = 1: the user tiles live in TENSOR memory (tcgen05.mma with the A operand from TMEM): the tensor core then reads
+// only the B tile from shared memory per instruction (64 B/cycle instead of the 128 B/cycle of the shared-memory form
+// at N = 128, which is the whole shared-memory bandwidth of the SM and capped the tensor pipe at ~85 %), and all of the
+// shared memory becomes B stages.  TMEM columns: 2 accumulators x 128 | MR x (d + 16) / 2 operand columns.
+template <int PASS, int KBLK, int KXT, int MR, int TS>
 __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmB,
                                                               const __grid_constant__ CUtensorMap tmAx,
                                                               const __grid_constant__ CUtensorMap tmBx, SweepArgs a,
                                                               int n_stages) {
     using namespace tc;
-    static_assert(MR >= 1 && MR <= MR_MAX && MR * TN <= TMEM_COLS, "accumulator index = resident user tile index");
-    constexpr int ACC = MR;
+    constexpr int ACC = TS ? 2 : MR;                             // TS: ring of two accumulators; else accumulator mr <-> user tile mr
+    constexpr int A_COLS = (KBLK * KB + (KXT ? KX : 0)) / 2;     // TS: 32-bit TMEM columns of one user tile
+    static_assert(MR >= 1 && MR <= MR_MAX && ACC * TN + (TS ? MR * A_COLS : 0) <= TMEM_COLS, "tensor memory budget");
     extern __shared__ unsigned char smem_raw[];
     // 1024 B alignment for the 128B-swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     constexpr uint32_t a1_bytes = A_KB_BYTES * KBLK + (KXT ? A_KX_BYTES : 0u);     // one user tile: K blocks + extra block
-    constexpr uint32_t a_bytes = a1_bytes * MR;                                    // MR user tiles stay resident for the whole sweep
+    constexpr uint32_t a_bytes = TS ? 0u : a1_bytes * MR;                          // MR user tiles stay resident for the whole sweep
     constexpr uint32_t b_bytes = B_KB_BYTES * KBLK + (KXT ? B_KX_BYTES : 0u);      // one B stage
     unsigned char* sA = smem;
     unsigned char* sB = smem + a_bytes;
@@ -380,7 +413,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
         for (int s = 0; s < ACC; ++s) { mbar_init(bar_tfull + 8 * s, 1); mbar_init(bar_tempty + 8 * s, EPI_WARPS); }
-        mbar_init(bar_afull, 1);
+        mbar_init(bar_afull, TS ? EPI_WARPS : 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == MMA_WARP) tmem_alloc(smem_u32(tmem_slot), TMEM_COLS);
@@ -395,7 +428,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
     if (warp == TMA_WARP) {
         // ===== TMA producer =====
         if (n_my > 0) {
-            if (elect_one()) {
+            if (!TS && elect_one()) {
                 mbar_expect_tx(bar_afull, a_bytes);
 #pragma unroll
                 for (int mr = 0; mr < MR; ++mr) {
@@ -434,27 +467,75 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             for (int i = 0; i < n_my; ++i) {
                 mbar_wait(bar_full + 8 * s, ph);
                 const uint32_t b_lo = b_lo0 + (uint32_t)s * (b_bytes >> 4);
-                const uint32_t aph = (uint32_t)i & 1u;
+                if (!TS && (MR % 2) == 0 && a.interleave) {
+                    // two user tiles at a time, their MMAs interleaved: consecutive instructions then never accumulate
+                    // into the same TMEM tile (back-to-back dependent MMAs leave a bubble in the tensor pipe)
+                    const uint32_t aph = (uint32_t)i & 1u;
+#pragma unroll
+                    for (int mp = 0; mp < MR; mp += 2) {
+                        mbar_wait(bar_tempty + 8 * mp, aph ^ 1u);
+                        mbar_wait(bar_tempty + 8 * (mp + 1), aph ^ 1u);
+                        fence_after();
+                        if (elect_one()) {
+                            const uint32_t d0 = tmem_base + (uint32_t)mp * TN, d1 = d0 + TN;
+                            const uint32_t am0 = a_lo + (uint32_t)mp * (a1_bytes >> 4), am1 = am0 + (a1_bytes >> 4);
+#pragma unroll
+                            for (int kb = 0; kb < KBLK; ++kb)
+#pragma unroll
+                                for (int k = 0; k < KB / 16; ++k) {
+                                    const uint64_t bd = make_desc_hl(DESC_HI_SW128, b_lo + kb * (B_KB_BYTES >> 4) + k * 2);
+                                    umma_bf16(d0, make_desc_hl(DESC_HI_SW128, am0 + kb * (A_KB_BYTES >> 4) + k * 2), bd, IDESC, (kb | k) ? 1u : 0u);
+                                    umma_bf16(d1, make_desc_hl(DESC_HI_SW128, am1 + kb * (A_KB_BYTES >> 4) + k * 2), bd, IDESC, (kb | k) ? 1u : 0u);
+                                }
+                            if (KXT) {
+                                const uint64_t bd = make_desc_hl(DESC_HI_SW32, b_lo + KBLK * (B_KB_BYTES >> 4));
+                                umma_bf16(d0, make_desc_hl(DESC_HI_SW32, am0 + KBLK * (A_KB_BYTES >> 4)), bd, IDESC, 1u);
+                                umma_bf16(d1, make_desc_hl(DESC_HI_SW32, am1 + KBLK * (A_KB_BYTES >> 4)), bd, IDESC, 1u);
+                            }
+                            if (mp == MR - 2) umma_commit(bar_empty + 8 * s);
+                            umma_commit(bar_tfull + 8 * mp);
+                            umma_commit(bar_tfull + 8 * (mp + 1));
+                        }
+                        __syncwarp();
+                    }
+                } else {
 #pragma unroll
                 for (int mr = 0; mr < MR; ++mr) {
-                    mbar_wait(bar_tempty + 8 * mr, aph ^ 1u);
+                    const int sub = i * MR + mr;
+                    const int acc = TS ? (sub & 1) : mr;
+                    const uint32_t aph = TS ? (uint32_t)(sub >> 1) & 1u : (uint32_t)i & 1u;
+                    mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
                     fence_after();
                     if (elect_one()) {
-                        const uint32_t d_tmem = tmem_base + (uint32_t)mr * TN;
-                        const uint32_t am = a_lo + (uint32_t)mr * (a1_bytes >> 4);
+                        const uint32_t d_tmem = tmem_base + (uint32_t)acc * TN;
+                        if (TS) {
+                            const uint32_t at = tmem_base + (uint32_t)(ACC * TN + mr * A_COLS);     // 8 columns per K step of 16
 #pragma unroll
-                        for (int kb = 0; kb < KBLK; ++kb)
+                            for (int kb = 0; kb < KBLK; ++kb)
 #pragma unroll
-                            for (int k = 0; k < KB / 16; ++k)    // UMMA K = 16 bf16 = 32 B inside the 128 B swizzle row
-                                umma_bf16(d_tmem, make_desc_hl(DESC_HI_SW128, am + kb * (A_KB_BYTES >> 4) + k * 2),
-                                          make_desc_hl(DESC_HI_SW128, b_lo + kb * (B_KB_BYTES >> 4) + k * 2), IDESC, (kb | k) ? 1u : 0u);
-                        if (KXT)                                 // + x_j: (1, 1, 1, 0...) . (x_hi, x_mid, x_lo, 0...)
-                            umma_bf16(d_tmem, make_desc_hl(DESC_HI_SW32, am + KBLK * (A_KB_BYTES >> 4)),
-                                      make_desc_hl(DESC_HI_SW32, b_lo + KBLK * (B_KB_BYTES >> 4)), IDESC, 1u);
+                                for (int k = 0; k < KB / 16; ++k)
+                                    umma_bf16_ts(d_tmem, at + (uint32_t)(kb * (KB / 2) + k * 8),
+                                                 make_desc_hl(DESC_HI_SW128, b_lo + kb * (B_KB_BYTES >> 4) + k * 2), IDESC, (kb | k) ? 1u : 0u);
+                            if (KXT)
+                                umma_bf16_ts(d_tmem, at + (uint32_t)(KBLK * (KB / 2)),
+                                             make_desc_hl(DESC_HI_SW32, b_lo + KBLK * (B_KB_BYTES >> 4)), IDESC, 1u);
+                        } else {
+                            const uint32_t am = a_lo + (uint32_t)mr * (a1_bytes >> 4);
+#pragma unroll
+                            for (int kb = 0; kb < KBLK; ++kb)
+#pragma unroll
+                                for (int k = 0; k < KB / 16; ++k)    // UMMA K = 16 bf16 = 32 B inside the 128 B swizzle row
+                                    umma_bf16(d_tmem, make_desc_hl(DESC_HI_SW128, am + kb * (A_KB_BYTES >> 4) + k * 2),
+                                              make_desc_hl(DESC_HI_SW128, b_lo + kb * (B_KB_BYTES >> 4) + k * 2), IDESC, (kb | k) ? 1u : 0u);
+                            if (KXT)                                 // + x_j: (1, 1, 1, 0...) . (x_hi, x_mid, x_lo, 0...)
+                                umma_bf16(d_tmem, make_desc_hl(DESC_HI_SW32, am + KBLK * (A_KB_BYTES >> 4)),
+                                          make_desc_hl(DESC_HI_SW32, b_lo + KBLK * (B_KB_BYTES >> 4)), IDESC, 1u);
+                        }
                         if (mr == MR - 1) umma_commit(bar_empty + 8 * s);   // B stage may be refilled once these MMAs retire
-                        umma_commit(bar_tfull + 8 * mr);                    // accumulator ready for the epilogue
+                        umma_commit(bar_tfull + 8 * acc);                   // accumulator ready for the epilogue
                     }
                     __syncwarp();
+                }
                 }
                 if (++s == n_stages) { s = 0; ph ^= 1; }
             }
@@ -477,6 +558,34 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             my_cand[mr] = PASS == 1 ? a.cand + (row[mr] * a.n_seg + seg) * a.seg_cap : nullptr;
             n_local[mr] = 0;
         }
+        if (TS && n_my > 0) {
+            // user tiles -> tensor memory: thread (q, lane) owns TMEM lane 32q + lane = row 32q + lane of every tile; the
+            // tiles are dealt to the two column-half warp groups.  K element k of the row -> column k / 2, half k % 2.
+            for (int mr = h; mr < MR; mr += EPI_G) {
+                const uint32_t at = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(ACC * TN + mr * A_COLS);
+                const uint4* src = reinterpret_cast<const uint4*>(a.Ub + row[mr] * (int64_t)(KBLK * KB));
+                uint32_t w[64];
+#pragma unroll
+                for (int kb = 0; kb < KBLK; ++kb) {
+#pragma unroll
+                    for (int x = 0; x < 8; ++x) {
+                        const uint4 v = __ldg(src + kb * 8 + x);
+                        w[4 * x + 0] = v.x; w[4 * x + 1] = v.y; w[4 * x + 2] = v.z; w[4 * x + 3] = v.w;
+                    }
+                    tmem_st32(at + (uint32_t)(kb * 32), w);
+                }
+                if (KXT) {
+                    const uint4* sx = reinterpret_cast<const uint4*>(a.Ux + row[mr] * (int64_t)KX);
+                    const uint4 v0 = __ldg(sx), v1 = __ldg(sx + 1);
+                    w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
+                    tmem_st8(at + (uint32_t)(KBLK * 32), w);
+                }
+            }
+            tmem_st_wait();
+            fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_afull);
+        }
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * EPI_COLS);
         float tn_next = n_my > 0 ? __ldg(a.tile_inorm + t_first) : 0.f;
         float tcol_next = (KXT && n_my > 0) ? __ldg(a.tile_col + t_first) : 0.f;
@@ -492,8 +601,9 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             const bool tail = j0 + EPI_COLS > a.N;
 #pragma unroll
             for (int mr = 0; mr < MR; ++mr) {
-                const int acc = mr;
-                const uint32_t aph = (uint32_t)i & 1u;
+                const int sub = i * MR + mr;
+                const int acc = TS ? (sub & 1) : mr;
+                const uint32_t aph = TS ? (uint32_t)(sub >> 1) & 1u : (uint32_t)i & 1u;
                 float E = fmaf(unAB[mr], tn, eb);                    // |v_j - its real-number meaning| <= E on this tile
                 E = fmaf(E, 2e-6f, E);
                 mbar_wait(bar_tfull + 8 * acc, aph);
@@ -1080,9 +1190,11 @@ static int env_int(const char* name, int dflt) {
 size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     using namespace tc;
     static_assert(TM == TN, "one tensor-map box shape serves both operands");
-    // user tiles per CTA: 3 leaves room for a third B stage at d = 128 (the TMA round trip then hides behind two tiles
-    // of MMAs), 4 reads every B tile from L2 for 512 instead of 384 users
-    p->mr = env_int("PDA_TC_MR", a.d == 128 ? 3 : 4) == 3 ? 3 : 4;
+    // user tiles per CTA: 4 in shared memory (the default) or 3 in tensor memory (PDA_TC_TS=1, the TS form of the MMA).
+    // Measured equal within 2 % on the synthetic set (pass B 2.76 vs 2.82 ms): the tensor pipe, not the shared-memory
+    // operand fetch, bounds both -- a 128x128x16 UTCHMMA costs ~78 cycles instead of the nominal 64.
+    p->ts = env_int("PDA_TC_TS", 0) ? 1 : 0;
+    p->mr = p->ts ? 3 : 4;
     const int MR = p->mr;
     p->M_pad = (a.M + TM * MR - 1) / (TM * MR) * (TM * MR);
     p->N_pad = (a.N + TN - 1) / TN * TN;
@@ -1158,32 +1270,32 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
 
 struct SweepMaps { CUtensorMap A, B, Ax, Bx; };
 
-template <int PASS, int KBLK, int KXT, int MR>
+template <int PASS, int KBLK, int KXT, int MR, int TS>
 static int launch_sweep_t(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p, int m_tiles, cudaStream_t st) {
     using namespace tc;
     const int kblocks = s.d / KB;
-    const size_t a_bytes = ((size_t)A_KB_BYTES * kblocks + (s.kx ? A_KX_BYTES : 0)) * MR;
+    const size_t a_bytes = TS ? 0 : ((size_t)A_KB_BYTES * kblocks + (s.kx ? A_KX_BYTES : 0)) * MR;
     const size_t b_bytes = (size_t)B_KB_BYTES * kblocks + (s.kx ? B_KX_BYTES : 0);
     const size_t fixed = 1024 + 256 + 64;
     int n_stages = (int)((227 * 1024 - fixed - a_bytes) / b_bytes);
-    if (n_stages > 6) n_stages = 6;
+    if (n_stages > 8) n_stages = 8;
     if (n_stages < 2) return 1;
     const size_t smem = fixed + a_bytes + (size_t)n_stages * b_bytes;
-    if (cudaFuncSetAttribute(tc_sweep_kernel<PASS, KBLK, KXT, MR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(tc_sweep_kernel<PASS, KBLK, KXT, MR, TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return 2;
     dim3 grid(m_tiles, p.splits);
-    tc_sweep_kernel<PASS, KBLK, KXT, MR><<<grid, NT, smem, st>>>(tm.A, tm.B, tm.Ax, tm.Bx, s, n_stages);
+    tc_sweep_kernel<PASS, KBLK, KXT, MR, TS><<<grid, NT, smem, st>>>(tm.A, tm.B, tm.Ax, tm.Bx, s, n_stages);
     return 0;
 }
 
 template <int PASS>
 static int launch_sweep(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p, int m_tiles, cudaStream_t st) {
-    if (p.mr == 3) {
-        if (s.d == 64) return s.kx ? launch_sweep_t<PASS, 1, 1, 3>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 1, 0, 3>(tm, s, p, m_tiles, st);
-        return s.kx ? launch_sweep_t<PASS, 2, 1, 3>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 2, 0, 3>(tm, s, p, m_tiles, st);
+    if (p.ts) {      // user tiles in tensor memory: 3 per CTA
+        if (s.d == 64) return s.kx ? launch_sweep_t<PASS, 1, 1, 3, 1>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 1, 0, 3, 1>(tm, s, p, m_tiles, st);
+        return s.kx ? launch_sweep_t<PASS, 2, 1, 3, 1>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 2, 0, 3, 1>(tm, s, p, m_tiles, st);
     }
-    if (s.d == 64) return s.kx ? launch_sweep_t<PASS, 1, 1, 4>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 1, 0, 4>(tm, s, p, m_tiles, st);
-    return s.kx ? launch_sweep_t<PASS, 2, 1, 4>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 2, 0, 4>(tm, s, p, m_tiles, st);
+    if (s.d == 64) return s.kx ? launch_sweep_t<PASS, 1, 1, 4, 0>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 1, 0, 4, 0>(tm, s, p, m_tiles, st);
+    return s.kx ? launch_sweep_t<PASS, 2, 1, 4, 0>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 2, 0, 4, 0>(tm, s, p, m_tiles, st);
 }
 
 // prep shared by the filter pipeline and the diagnostics entry: bf16 operands, norms, tile maxima, tensor maps
@@ -1226,6 +1338,7 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
     s->tiles_per_split = p.tiles_per_split; s->se = p.se;
     const float cA = 1.02f / 256.0f + (float)a.d / 2097152.0f, cB = (float)(a.d / 16 + 5) / 524288.0f;
     s->cAB = cA + cB; s->cB = cB;
+    s->Ub = Ub; s->Ux = Ux; s->interleave = env_int("PDA_TC_IL", 0);      // measured: no gain (2.89 vs 2.76 ms)
     s->unorm = unorm; s->tile_inorm = tnorm; s->tile_col = kx ? tcolmax : nullptr;
     s->cmax = (float*)(b + p.o_cmax); s->n_c = p.n_c; s->cw = p.cw;
     s->tau = (float*)(b + p.o_tau); s->cand = (int32_t*)(b + p.o_cand); s->cnt = (int32_t*)(b + p.o_cnt);
@@ -1237,7 +1350,7 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
 // prep_items = false: the item operands in `scratch` were prepared by an earlier block of the same call (same tables,
 // pop, bias).
 // `scratch` = device buffer of tc_scratch_bytes(); results -> a.ids_out / a.scores_out.
-int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, bool prep_items, cudaStream_t st) {
+int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, bool prep_items, cudaStream_t st, cudaEvent_t* ev) {
     using namespace tc;
     if (!tc_supported(a)) return 1;
     char* b = (char*)scratch;
@@ -1251,13 +1364,17 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, bool 
     int rc = tc_prepare(a, b, p, &tm, &s, prep_items, st);
     if (rc) return rc;
 
+    if (ev) cudaEventRecord(ev[0], st);
     rc = launch_sweep<0>(tm, s, p, m_tiles, st);
+    if (ev) cudaEventRecord(ev[1], st);
     if (rc) return 10 + rc;
     const size_t tau_smem = (size_t)4 * (p.n_c + 384) * 4;
     if (cudaFuncSetAttribute(tc_tau_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tau_smem) != cudaSuccess) return 15;
     tc_tau_select_kernel<<<(unsigned)((p.M_pad + 3) / 4), 128, tau_smem, st>>>(s.cmax, p.n_c, p.n_valid, a.M, p.M_pad, p.se, p.cw, a.users,
                                                                                a.mask_indptr, a.mask_items, a.K, nflag + 1, tau);
+    if (ev) cudaEventRecord(ev[2], st);
     rc = launch_sweep<1>(tm, s, p, m_tiles, st);
+    if (ev) cudaEventRecord(ev[3], st);
     if (rc) return 20 + rc;
 
     RescoreArgs r;

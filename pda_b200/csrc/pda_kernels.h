@@ -71,7 +71,7 @@ struct EvalArgs {
 // plan + scratch layout of the tensor-core filter (pda_eval_tc.cu)
 struct TcPlan {
     int64_t M_pad, N_pad;
-    int n_tiles, mr, se, cw, n_c, n_valid, splits, tiles_per_split, n_seg, seg_cap, rc;
+    int n_tiles, mr, ts, se, cw, n_c, n_valid, splits, tiles_per_split, n_seg, seg_cap, rc;
     size_t o_Ib, o_Ub, o_Ix, o_Ux, o_inorm, o_unorm, o_tnorm, o_tcolmax, o_targ, o_tcol2, o_cmax, o_tau, o_cnt, o_cand, o_flag, o_frows, o_fusers, o_nflag, o_clist, o_ckeys, o_ccount, o_work, o_nwork;
 };
 
@@ -92,7 +92,9 @@ void launch_temp_item_bias(const float* ub, const float* ib, int64_t n_items, in
 int launch_recommend_exact(const EvalArgs& a, cudaStream_t st);
 bool tc_supported(const EvalArgs& a);
 size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* plan);
-int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& plan, bool prep_items, cudaStream_t st);
+// ev: optional 4 events recorded around the sampled sweep (ev[0], ev[1]) and the full sweep (ev[2], ev[3])
+int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& plan, bool prep_items, cudaStream_t st,
+                        cudaEvent_t* ev = nullptr);
 int launch_tc_debug_dense(const EvalArgs& a, void* scratch, const TcPlan& plan, float* dense, cudaStream_t st);
 void launch_metrics(const int32_t* ids, int64_t M, int Kkeep, const int32_t* eval_users, const int64_t* truth_indptr,
                     const int32_t* truth_items, const int32_t* Ks, int nK, double* out, cudaStream_t st);

@@ -85,7 +85,7 @@ class PDAModel:
     def synchronize(self):
         check(self.lib.pda_synchronize(self._h))
 
-    PROF_KINDS = ("sampler", "bpr_step", "adam", "eval_exact", "eval_tensor", "adam_catchup")
+    PROF_KINDS = ("sampler", "bpr_step", "adam", "eval_exact", "eval_tensor", "adam_catchup", "eval_sweep_a", "eval_sweep_b")
 
     def profile(self, on=True):
         check(self.lib.pda_profile_enable(self._h, 1 if on else 0))
