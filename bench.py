@@ -238,7 +238,9 @@ def run_ours(a):
 
     # ---- eval: all-items scoring + pop adjust + mask + top-50 (pairs/s) ----
     ev = None
-    if not a.no_eval and rank == 0:
+    if not a.no_eval:
+        # every rank scores eval_users of ITS user shard against all (replicated) items: no exchange on the data path
+        # (pda_b200.parallel.ShardedEvaluator adds the one metric-sum all-reduce); aggregate = world x pairs / max time
         Me = min(a.eval_users, users_local)
         eu = np.arange(Me, dtype=np.int32)
         pop_e = synth.eval_pop_torch(ds["pop"], GAMMA).cpu().numpy()
@@ -250,20 +252,27 @@ def run_ours(a):
         pr = model.profile_read()
         model.profile(False)
         kms = pr["eval_exact"][0] + pr["eval_tensor"][0]
-        pairs = Me * a.items
+        if world > 1:
+            tk = torch.tensor([kms, wall], device=dev, dtype=torch.float64)
+            dist.all_reduce(tk, op=dist.ReduceOp.MAX)
+            kms_max, wall = float(tk[0].item()), float(tk[1].item())
+        else:
+            kms_max = kms
+        pairs = Me * a.items                                  # per rank
         flop = pairs * 2 * d                                  # 2*d FLOP per scored (user, item) pair
         sb_ms, sb_n = pr["eval_sweep_b"]
         sa_ms, sa_n = pr["eval_sweep_a"]
         tr = ncu_traffic()
         same = (a.items, d) == (1_000_000, 128)
-        ev = {"metric": "eval_user_item_pairs_per_sec", "value": pairs / (kms * 1e-3), "unit": "pairs/s",
-              "e2e_value": pairs / wall, "users": Me, "items": a.items, "K": 50, "rec_type": "condition",
+        ev = {"metric": "eval_user_item_pairs_per_sec", "value": world * pairs / (kms_max * 1e-3), "unit": "pairs/s",
+              "e2e_value": world * pairs / wall, "n_gpus": world, "users_per_gpu": Me, "items": a.items, "K": 50,
+              "rec_type": "condition",
               "backend": "exact fp32 CUDA-core scorer" if pr["eval_tensor"][1] == 0 else
               "tcgen05 bf16 filter (kind::f16, fp32 accumulate in TMEM, pop folded into the GEMM) + exact fp32 rescoring "
               "of the certified candidates",
               "filter_stats": model.tc_last_stats() if pr["eval_tensor"][1] else None,
               "kernel_ms": kms,
-              # whole pipeline (prep + sampled sweep + tau + full sweep + rescoring) against the tensor peak
+              # whole pipeline (prep + sampled sweep + tau + full sweep + rescoring) against the tensor peak, rank 0
               "roofline": {"bound": "tensor", "achieved": flop / (kms * 1e-3) / 1e12, "peak": pk["bf16_sus"],
                            "unit": "TFLOP/s", "frac": flop / (kms * 1e-3) / 1e12 / pk["bf16_sus"],
                            "traffic": None, "peak_source": pk["src"] + " sustained bf16 (kernels timed inside a long step)"}}

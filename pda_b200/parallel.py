@@ -1,4 +1,4 @@
-"""Data-parallel driver of the train step over the GPUs of one box.
+"""Data-parallel drivers of the train step and of the evaluation over the GPUs of one box.
 
 Partition: USERS are split into contiguous shards, one per rank; every rank samples its B triples from
 its own users (rank-local sampling), so user rows, user gradients and the user table's Adam state never
@@ -103,3 +103,38 @@ class ShardedTrainer:
         m.forward_backward_device(B, stream)
         self._exchange_and_apply(stream)
         return m.read_loss(stream)
+
+
+class ShardedEvaluator:
+    """Evaluation over user shards: every rank scores ITS eval users against all items (the item table is
+    replicated, so the recommender needs no exchange), reduces Recall / Precision / NDCG / Hit sums on its GPU, and one
+    all-reduce of the 4 x len(Ks) sums (+ the user count) gives the global means -- train_new_api.py:741-778 averaged
+    over all ranks' users.  `users` are rank-local row ids of the model's user table; `truth_*` is the CSR of the
+    rank's own eval users."""
+
+    def __init__(self, model, world=1, rank=0, reducer=None):
+        self.model, self.world, self.rank = model, int(world), int(rank)
+        self._reduce = reducer
+        if self.world > 1 and reducer is None:
+            import torch.distributed as dist
+            self._reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    def eval(self, users, truth_indptr, truth_items, Ks, rec_type="main_branch", pos_pop=None, K=50, device=None):
+        import numpy as np
+        Ks = list(Ks)
+        keys = ("precision", "recall", "ndcg", "hit_ratio")
+        sums = np.zeros(4 * len(Ks) + 1, dtype=np.float64)
+        if len(users):
+            ids = self.model.do_recommendation(users, None, rec_type, pos_pop=pos_pop, K=K)
+            s = self.model.metrics_sum(ids, users, truth_indptr, truth_items, Ks)
+            sums[:-1] = np.concatenate([np.asarray(s[k], dtype=np.float64) for k in keys])
+            sums[-1] = len(users)
+        if self.world > 1:
+            import torch
+            t = torch.from_numpy(sums)
+            if device is not None:
+                t = t.to(device)
+            self._reduce(t)
+            sums = t.cpu().numpy()
+        n = max(sums[-1], 1.0)
+        return {k: sums[i * len(Ks):(i + 1) * len(Ks)] / n for i, k in enumerate(keys)}

@@ -150,3 +150,92 @@ def test_two_ranks_equal_one_process_on_the_union_batch():
         assert np.abs(Ur - om.U[lo:hi]).max() <= 2e-5 * np.abs(om.U).max()
         for got, want in zip(losses, ref_losses):
             assert np.allclose(got, want, rtol=1e-5)
+
+
+# ---------------------------------------------------------------------------------------------
+# sharded evaluation: per-rank metric sums + one all-reduce = the single-process means
+# ---------------------------------------------------------------------------------------------
+class EvalStandIn:
+    """do_recommendation / metrics_sum of PDAModel on the CPU oracle (rank-local user ids)."""
+
+    def __init__(self, U, I, indptr, items):
+        from oracle import pda_oracle as po
+        self.po, self.U, self.I, self.indptr, self.items = po, U, I, indptr, items
+
+    def do_recommendation(self, users, items=None, rec_type="main_branch", pos_pop=None, K=50):
+        return self.po.recommend(self.U, self.I, np.asarray(users, dtype=np.int32), rec_type, K, self.indptr, self.items, pop=pos_pop)
+
+    def metrics_sum(self, ids, eval_users, truth_indptr, truth_items, Ks):
+        return _metrics_sum(self.po, ids, eval_users, truth_indptr, truth_items, Ks)
+
+
+def _metrics_sum(po, ids, eval_users, truth_indptr, truth_items, Ks):
+    res = {k: np.zeros(len(Ks)) for k in ("precision", "recall", "ndcg", "hit_ratio")}
+    for r, u in enumerate(eval_users):
+        one = po.get_performance(truth_items[truth_indptr[u]:truth_indptr[u + 1]], ids[r], Ks)
+        for k in res:
+            res[k] += one[k]
+    return res
+
+
+def _eval_problem():
+    from oracle import pda_oracle as po
+    rng = np.random.default_rng(5)
+    n_users, n_items, d = 90, 120, 8
+    U = rng.normal(0, 1, (n_users, d)).astype(np.float32)
+    I = rng.normal(0, 1, (n_items, d)).astype(np.float32)
+    uid = np.repeat(np.arange(n_users), 6); iid = rng.integers(0, n_items, len(uid))
+    key = np.unique(uid.astype(np.int64) * n_items + iid)
+    tr_ptr, tr_items, _ = po.build_csr(n_users, key // n_items, key % n_items)
+    uid2 = np.repeat(np.arange(n_users), 4); iid2 = rng.integers(0, n_items, len(uid2))
+    key2 = np.unique(uid2.astype(np.int64) * n_items + iid2)
+    te_ptr, te_items, _ = po.build_csr(n_users, key2 // n_items, key2 % n_items)
+    pop = rng.random(n_items).astype(np.float32)
+    return U, I, tr_ptr, tr_items, te_ptr, te_items, pop
+
+
+def _csr_slice(indptr, items, lo, hi):
+    return (indptr[lo:hi + 1] - indptr[lo]).astype(np.int64), items[indptr[lo]:indptr[hi]]
+
+
+def _eval_worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    from pda_b200.parallel import ShardedEvaluator, shard_range
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        U, I, tr_ptr, tr_items, te_ptr, te_items, pop = _eval_problem()
+        lo, hi = shard_range(len(U), world, rank)
+        mp_, mi_ = _csr_slice(tr_ptr, tr_items, lo, hi)
+        tp_, ti_ = _csr_slice(te_ptr, te_items, lo, hi)
+        ev = ShardedEvaluator(EvalStandIn(U[lo:hi], I, mp_, mi_), world, rank)
+        users = np.arange(hi - lo, dtype=np.int32)[:: 2 if rank == 0 else 1]       # uneven shards
+        out = ev.eval(users, tp_, ti_, [5, 20], rec_type="condition", pos_pop=pop, K=20)
+        q.put((rank, lo, users + lo, out))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_eval_equals_single_process():
+    import torch.multiprocessing as mp
+    from oracle import pda_oracle as po
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    world = 2
+    procs = [ctx.Process(target=_eval_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda x: x[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    U, I, tr_ptr, tr_items, te_ptr, te_items, pop = _eval_problem()
+    users = np.concatenate([r[2] for r in res]).astype(np.int32)
+    ids = po.recommend(U, I, users, "condition", 20, tr_ptr, tr_items, pop=pop)
+    want = _metrics_sum(po, ids, users, te_ptr, te_items, [5, 20])
+    for r in res:
+        for k in ("precision", "recall", "ndcg", "hit_ratio"):
+            assert np.allclose(r[3][k], np.asarray(want[k]) / len(users), rtol=1e-12, atol=1e-15), k
