@@ -136,6 +136,8 @@ def run_ours(a):
     if world != a.gpus and world > 1:
         a.gpus = world
     torch.cuda.set_device(local)
+    if world > 1 and os.environ.get("NCCL_DEBUG", "").upper() != "INFO":
+        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL_DEBUG=VERSION prints a banner on stdout next to the JSON line
     if world > 1:
         # high-priority NCCL stream: the item-gradient all-reduce must get its CTAs although the (persistent, full-
         # occupancy) Adam kernel of the rank-local half becomes runnable at the same instant

@@ -3,9 +3,12 @@
 Partition: USERS are split into contiguous shards, one per rank; every rank samples its B triples from
 its own users (rank-local sampling), so user rows, user gradients and the user table's Adam state never
 leave the GPU.  The ITEM table (small: n_items x d) is replicated; its gradient is the one real exchange
-step: an NCCL all-reduce (sum) of the dense item-gradient accumulator between the fused BPR kernel and
-the Adam sweep, after which every rank applies the identical item update.  The result equals a
-single-process step on the union batch of world*B triples (loss mean and L2 divisor use the global batch).
+step.  Default ("scatter", when n_items divides by the world size): NCCL reduce-scatter of the dense
+item-gradient accumulator -> every rank runs the Adam sweep on ITS row slice only (1/world of the sweep, and
+only that slice of the item Adam slots is live) -> NCCL all-gather of the updated rows, waited for right
+before the next step's kernel reads the table.  Fallback ("allreduce"): all-reduce of the gradient in row
+chunks pipelined with the full dense sweep on every rank.  Either way the result equals a single-process
+step on the union batch of world*B triples (loss mean and L2 divisor use the global batch).
 
 torch.distributed is plumbing: it owns the NCCL communicator and the stream; the kernels are the library's.
 With world == 1 this class adds nothing to the single-GPU path.
@@ -29,9 +32,15 @@ def shard_range(n, world, rank):
 
 
 class ShardedTrainer:
-    def __init__(self, model, world=1, rank=0, reducer=None, chunks=4):
-        """reducer(tensor) -> None sums `tensor` in place over ranks (default: torch.distributed.all_reduce)."""
+    def __init__(self, model, world=1, rank=0, reducer=None, chunks=4, exchange=None):
+        """reducer(tensor) -> None sums `tensor` in place over ranks (default: torch.distributed.all_reduce).
+        exchange: "scatter" | "allreduce" | None (= $PDA_DP_EXCHANGE, else scatter where it applies)."""
+        import os
         self.model, self.world, self.rank = model, int(world), int(rank)
+        self._wi = None
+        self._pending = None
+        self._own = None
+        exchange = exchange or os.environ.get("PDA_DP_EXCHANGE", "scatter")
         if int(world) > 1 and getattr(model, "train", "") == "temp_pop":
             raise NotImplementedError("data-parallel training covers BPRMF / PD / PDG (the bias tables of BPR(t)-pop are not exchanged)")
         self._gi = self._acc = None
@@ -56,6 +65,11 @@ class ShardedTrainer:
                 self._gi = torch.as_tensor(_DevArray(model.grad_ptr("item_embedding"), (model.n_items, model.emb_dim),
                                                      "<f4"), device=dev)
                 self._acc = torch.as_tensor(_DevArray(model.loss_acc_ptr(), (2,), "<f8"), device=dev)
+                if exchange == "scatter" and self._async_reduce is not None and model.n_items % self.world == 0:
+                    self._wi = torch.as_tensor(_DevArray(model.table_ptr("item_embedding"), (model.n_items, model.emb_dim),
+                                                         "<f4"), device=dev)
+                    rows = model.n_items // self.world
+                    self._own = (self.rank * rows, (self.rank + 1) * rows)
 
     def _exchange(self):
         self._reduce(self._gi)     # dense item-gradient block, summed over ranks (NVLink / NVSwitch)
@@ -68,6 +82,23 @@ class ShardedTrainer:
         if self._async_reduce is None:
             self._exchange()
             m.adam_apply(stream)
+            return
+        if self._own is not None:
+            import torch.distributed as dist
+            lo, hi = self._own
+            # in place: this rank's slice of the accumulator receives the sum over ranks of that slice
+            w_rs = dist.reduce_scatter_tensor(self._gi[lo:hi], self._gi, op=dist.ReduceOp.SUM, async_op=True)
+            wacc = self._async_reduce(self._acc)
+            m.adam_apply(stream, part=1)          # rank-local tables (nothing when the step kernel already did it)
+            w_rs.wait()                           # stream-level dependency, the host does not block
+            m.adam_dense_rows("item_embedding", lo, hi, stream)      # consumes and zeroes rows [lo, hi) of the accumulator
+            if lo > 0:
+                self._gi[:lo].zero_()             # the other slices hold this rank's partial sums
+            if hi < m.n_items:
+                self._gi[hi:].zero_()
+            self._pending = dist.all_gather_into_tensor(self._wi, self._wi[lo:hi], async_op=True)
+            wacc.wait()
+            m.adam_apply(stream, part=8)
             return
         # the item gradient travels in row chunks: chunk k's all-reduce overlaps the dense Adam sweep of chunk k-1
         # (and, first of all, the rank-local half of the optimizer)
@@ -90,9 +121,17 @@ class ShardedTrainer:
             return
         m.set_global_batch(B * self.world)
         for k in range(n_steps):
-            m.sample_batch(seed, epoch, step0 + k, B, stream, fetch=False)
+            m.sample_batch(seed, epoch, step0 + k, B, stream, fetch=False)      # overlaps the all-gather of the last step
+            self.finish()
             m.forward_backward_device(B, stream)
             self._exchange_and_apply(stream)
+        self.finish()
+
+    def finish(self):
+        """the item table is complete on this rank's compute stream (all-gather of the last step done)"""
+        if self._pending is not None:
+            self._pending.wait()
+            self._pending = None
 
     def train_step_host(self, users, pos, neg, pos_pop=None, neg_pop=None, stream=0):
         m = self.model
@@ -100,8 +139,10 @@ class ShardedTrainer:
             return m.train_step(users, pos, neg, pos_pop, neg_pop)
         m.set_global_batch(len(users) * self.world)
         B = m.stage_batch(users, pos, neg, pos_pop, neg_pop, stream)
+        self.finish()
         m.forward_backward_device(B, stream)
         self._exchange_and_apply(stream)
+        self.finish()
         return m.read_loss(stream)
 
 

@@ -1,5 +1,6 @@
-"""2-GPU check (NCCL) of the data-parallel train step: user shards + replicated item table + item-gradient all-reduce
-overlapped with the rank-local Adam half must equal ONE process stepping on the union batch (CPU oracle).
+"""2-GPU check (NCCL) of the data-parallel train step: user shards + replicated item table + item-gradient exchange
+(reduce-scatter -> sliced Adam -> all-gather, or the chunked all-reduce) must equal ONE process stepping on the union
+batch (CPU oracle).
 Skipped on boxes with fewer than 2 GPUs (run it with `gpurun --gpus 2`)."""
 import os
 import socket
@@ -17,7 +18,7 @@ def _n_gpus():
     return pda_b200.load().pda_device_count()
 
 
-def _worker(rank, world, port, q, adam_mode):
+def _worker(rank, world, port, q, adam_mode, exchange):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -38,7 +39,7 @@ def _worker(rank, world, port, q, adam_mode):
         m.set_table("item_embedding", I)
         if adam_mode == "lazy":
             m.set_adam_mode("lazy")       # the trainer narrows it to lazy users + dense (all-reduced) items
-        tr = ShardedTrainer(m, world, rank)
+        tr = ShardedTrainer(m, world, rank, exchange=exchange)
         stream = torch.cuda.current_stream().cuda_stream
         losses = []
         for step in range(6):
@@ -59,8 +60,8 @@ def _worker(rank, world, port, q, adam_mode):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("adam_mode", ["dense", "lazy"])
-def test_two_gpus_equal_one_process_on_the_union_batch(c_oracle, adam_mode):
+@pytest.mark.parametrize("adam_mode,exchange", [("dense", "scatter"), ("lazy", "scatter"), ("lazy", "allreduce")])
+def test_two_gpus_equal_one_process_on_the_union_batch(c_oracle, adam_mode, exchange):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -69,7 +70,7 @@ def test_two_gpus_equal_one_process_on_the_union_batch(c_oracle, adam_mode):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     world = 2
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, adam_mode)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, adam_mode, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=400) for _ in range(world)], key=lambda x: x[0])
