@@ -136,8 +136,11 @@ def run_ours(a):
     if world != a.gpus and world > 1:
         a.gpus = world
     torch.cuda.set_device(local)
-    if world > 1 and os.environ.get("NCCL_DEBUG", "").upper() != "INFO":
-        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL_DEBUG=VERSION prints a banner on stdout next to the JSON line
+    # stdout carries exactly ONE JSON line: everything else that writes to fd 1 from here on (NCCL's version banner
+    # under NCCL_DEBUG=VERSION/WARN, library chatter) goes to stderr; the line itself is written to the saved fd
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if world > 1:
         # high-priority NCCL stream: the item-gradient all-reduce must get its CTAs although the (persistent, full-
         # occupancy) Adam kernel of the rank-local half becomes runnable at the same instant
@@ -342,7 +345,8 @@ def run_ours(a):
                "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e, "eval": ev,
                "gpu_launches": int(step_n + adam_n + cat_n + samp_n + a.steps), "clocks": clocks.summary(),
                "last_loss": [float(x) for x in loss]}
-        print(json.dumps(out))
+        json_out.write(json.dumps(out) + "\n")
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
