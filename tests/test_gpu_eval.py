@@ -197,3 +197,35 @@ def test_tensor_backend_rejects_unsupported_shapes(pda):
     ids = m.do_recommendation(np.arange(10, dtype=np.int32), None, "main_branch", K=10, backend="auto")   # exact kernel
     assert ids.shape == (10, 10)
     m.close()
+
+
+def test_recommend_tensor_negative_pop_and_single_user(pda, c_oracle):
+    """negative pops void the bounds of the filter (they assume pop >= 0): the conversion kernel raises a flag and every
+    row goes through the exact kernel; and a single-user call (1 real row in a 512-row block)."""
+    m, U, I, indptr, items, pop, rng = _setup(pda, 300, 6000, 64, seed=77, scale=2.0)
+    users = rng.permutation(300)[:200].astype(np.int32)
+    neg = pop.copy()
+    neg[rng.random(6000) < 0.01] *= -1.0
+    ids, sc = m.do_recommendation(users, None, "condition", pos_pop=neg, K=50, backend="tensor", return_scores=True)
+    st = m.tc_last_stats()
+    rid, rsc = c_oracle.recommend(U, I, users, "condition", 50, indptr, items, pop=neg)
+    assert np.array_equal(ids, rid) and np.array_equal(bits(sc), bits(rsc))
+    assert st["rows_exact_fallback"] == len(users), st
+    one = users[:1]
+    ids, sc = m.do_recommendation(one, None, "condition", pos_pop=pop, K=50, backend="tensor", return_scores=True)
+    rid, rsc = c_oracle.recommend(U, I, one, "condition", 50, indptr, items, pop=pop)
+    assert np.array_equal(ids, rid) and np.array_equal(bits(sc), bits(rsc))
+    m.close()
+
+
+@pytest.mark.parametrize("scale", [30.0, 1e-3])
+def test_recommend_tensor_extreme_score_scales(pda, c_oracle, scale):
+    """|s| ~ 100 (elu branch saturated, large bf16 error bound) and |s| ~ 1e-6 (everything decided by pop)."""
+    m, U, I, indptr, items, pop, rng = _setup(pda, 260, 7000, 128, seed=5, scale=scale)
+    users = np.arange(260, dtype=np.int32)
+    for rec_type in ("main_branch", "condition"):
+        ids, sc = m.do_recommendation(users, None, rec_type, pos_pop=pop, K=50, backend="tensor", return_scores=True)
+        rid, rsc = c_oracle.recommend(U, I, users, rec_type, 50, indptr, items, pop=pop)
+        assert np.array_equal(ids, rid), (rec_type, m.tc_last_stats())
+        assert np.array_equal(bits(sc), bits(rsc))
+    m.close()
