@@ -290,6 +290,84 @@ __global__ void __launch_bounds__(256) tc_tile_top2_kernel(const float* __restri
     if (lane == 0) { t1[t] = fmaxf(m1, 0.f); targ[t] = j1; t2[t] = fmaxf(m2, 0.f); }
 }
 
+// Pass A does not sample every se-th tile blindly: it takes the n_sel tiles whose items can score highest for ANY user --
+// key = max |w_j| + max |x_j| of the tile (large item norms / popularities: the usual MIPS "norm ranging" heuristic).
+// Their chunk maxima give a tau much closer to the true K-th best than a uniform sample of the same size, so the full
+// sweep delivers fewer candidates.  One block: radix select of the n_sel-th largest key, then an ordered compaction
+// (ascending tile id; ties at the threshold by lower id) -> order[0..n_sel), pos[tile] = position or -1.
+__global__ void __launch_bounds__(1024) tc_tile_select_kernel(const float* __restrict__ tn, const float* __restrict__ tcol, int n_tiles,
+                                                              int n_sel, int32_t* __restrict__ order, int32_t* __restrict__ pos) {
+    __shared__ int hist[256];
+    __shared__ int wsum[2][32];
+    __shared__ uint32_t s_prefix, s_mask;
+    __shared__ int s_need, s_base[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    auto key_of = [&](int t) -> uint32_t {
+        const float k = tn[t] + (tcol ? tcol[t] : 0.f);                  // >= 0
+        return __float_as_uint(k) | 0x80000000u;                         // order-preserving for non-negative floats
+    };
+    if (tid == 0) { s_prefix = 0; s_mask = 0; s_need = n_sel; }
+    __syncthreads();
+    for (int pass = 3; pass >= 0; --pass) {
+        const int shift = pass * 8;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        const uint32_t prefix = s_prefix, mask = s_mask;
+        for (int t = tid; t < n_tiles; t += 1024) {
+            const uint32_t k = key_of(t);
+            if ((k & mask) == prefix) atomicAdd(&hist[(k >> shift) & 255u], 1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int need = s_need, run = 0, bin = 255;
+            for (; bin > 0; --bin) { if (run + hist[bin] >= need) break; run += hist[bin]; }
+            s_need = need - run;
+            s_prefix = prefix | ((uint32_t)bin << shift);
+            s_mask = mask | (255u << shift);
+        }
+        __syncthreads();
+    }
+    const uint32_t kth = s_prefix;
+    const int need_eq = s_need;                                          // how many tiles with key == kth are taken
+    if (tid == 0) { s_base[0] = 0; s_base[1] = 0; }
+    __syncthreads();
+    for (int t0 = 0; t0 < n_tiles; t0 += 1024) {
+        const int t = t0 + tid;
+        const uint32_t k = t < n_tiles ? key_of(t) : 0u;
+        const int gt = k > kth, eq = t < n_tiles && k == kth;
+        int sg = gt, se_ = eq;                                           // inclusive scans over the block
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, sg, off), b = __shfl_up_sync(0xffffffffu, se_, off);
+            if (lane >= off) { sg += a; se_ += b; }
+        }
+        if (lane == 31) { wsum[0][wid] = sg; wsum[1][wid] = se_; }
+        __syncthreads();
+        if (wid == 0) {
+            int a = wsum[0][lane], b = wsum[1][lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int x = __shfl_up_sync(0xffffffffu, a, off), y = __shfl_up_sync(0xffffffffu, b, off);
+                if (lane >= off) { a += x; b += y; }
+            }
+            wsum[0][lane] = a; wsum[1][lane] = b;
+        }
+        __syncthreads();
+        const int gt_before = s_base[0] + (wid ? wsum[0][wid - 1] : 0) + sg - gt;      // exclusive ranks
+        const int eq_before = s_base[1] + (wid ? wsum[1][wid - 1] : 0) + se_ - eq;
+        if (t < n_tiles) {
+            const bool take = gt || (eq && eq_before < need_eq);
+            // position = taken tiles before this one: all greater ones + the equal ones that were taken
+            const int p = gt_before + min(eq_before, need_eq);
+            pos[t] = take ? p : -1;
+            if (take) order[p] = t;
+        }
+        __syncthreads();
+        if (tid == 0) { s_base[0] += wsum[0][31]; s_base[1] += wsum[1][31]; }
+        __syncthreads();
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // the sweep
 // ------------------------------------------------------------------------------------------------------------
@@ -299,7 +377,9 @@ struct SweepArgs {
     int d, kx;                 // kx = 1: the 16-column extra K block is present
     int n_tiles;               // item tiles of 128
     int tiles_per_split;       // each CTA of blockIdx.y sweeps [y * tiles_per_split, ...)
-    int se;                    // pass A: every se-th tile is sampled
+    int se;                    // pass A samples n_sel = ceil(n_tiles / se) tiles:
+    int n_sel, pos_per_split;  //   the tiles order[0..n_sel) (or, order == nullptr, every se-th tile); CTA y visits
+    const int32_t* order;      //   positions [y * pos_per_split, ...) of that list; chunk keys are indexed by position
     float cAB, cB;             // E = cAB * |u| * max|w_j| + cB * max|x_j|  (maxima over the tile)
     const __nv_bfloat16* Ub;   // [M_pad][d] bf16 user rows, [M_pad][16] extra block (TS mode reads them directly)
     const __nv_bfloat16* Ux;
@@ -405,10 +485,13 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
     const int m_blk = blockIdx.x;                                // MR consecutive 128-row user tiles
     const int t_begin = blockIdx.y * a.tiles_per_split;
     const int t_end = min(a.n_tiles, t_begin + a.tiles_per_split);
-    // tiles this CTA visits: pass A -> multiples of se; pass B -> all
-    const int step = PASS == 0 ? a.se : 1;
-    const int t_first = PASS == 0 ? ((t_begin + a.se - 1) / a.se) * a.se : t_begin;
-    const int n_my = t_first < t_end ? (t_end - t_first + step - 1) / step : 0;
+    // what this CTA visits: pass A -> positions of the sampled tile list; pass B -> all tiles of its range
+    const int p_first = PASS == 0 ? blockIdx.y * a.pos_per_split : t_begin;
+    const int n_my = PASS == 0 ? max(0, min(a.n_sel, p_first + a.pos_per_split) - p_first) : max(0, t_end - t_begin);
+    auto tile_of = [&](int i) -> int {
+        const int p = p_first + i;
+        return PASS == 0 ? (a.order ? __ldg(a.order + p) : p * a.se) : p;
+    };
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < n_stages; ++s) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
@@ -442,11 +525,13 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             __syncwarp();
             int s = 0;
             uint32_t ph = 0;
+            int t_next = tile_of(0);
             for (int i = 0; i < n_my; ++i) {
+                const int t = t_next;
+                if (i + 1 < n_my) t_next = tile_of(i + 1);               // the list lookup overlaps the wait
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);
                 if (elect_one()) {
                     mbar_expect_tx(bar_full + 8 * s, b_bytes);
-                    const int t = t_first + i * step;
                     const uint32_t bt = smem_u32(sB) + (uint32_t)s * b_bytes;
 #pragma unroll
                     for (int kb = 0; kb < KBLK; ++kb) tma_load_2d(bt + (uint32_t)kb * B_KB_BYTES, &tmB, bar_full + 8 * s, kb * KB, t * TN);
@@ -587,15 +672,19 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             if (lane == 0) mbar_arrive(bar_afull);
         }
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * EPI_COLS);
-        float tn_next = n_my > 0 ? __ldg(a.tile_inorm + t_first) : 0.f;
-        float tcol_next = (KXT && n_my > 0) ? __ldg(a.tile_col + t_first) : 0.f;
+        // two-deep prefetch: tile id of visit i + 2, bound terms of visit i + 1 (latency off the critical path)
+        int t_cur = n_my > 0 ? tile_of(0) : 0, t_nxt = n_my > 1 ? tile_of(1) : 0;
+        float tn_cur = n_my > 0 ? __ldg(a.tile_inorm + t_cur) : 0.f;
+        float tcol_cur = (KXT && n_my > 0) ? __ldg(a.tile_col + t_cur) : 0.f;
         for (int i = 0; i < n_my; ++i) {
-            const int t = t_first + i * step;
+            const int t = t_cur;
             const int64_t j0 = (int64_t)t * TN + h * EPI_COLS;       // first column of this thread's half
-            const float tn = tn_next, tcol = tcol_next;
-            if (i + 1 < n_my) {                                      // the next tile's bound terms: latency off the critical path
-                tn_next = __ldg(a.tile_inorm + t + step);
-                if (KXT) tcol_next = __ldg(a.tile_col + t + step);
+            const float tn = tn_cur, tcol = tcol_cur;
+            if (i + 1 < n_my) {
+                t_cur = t_nxt;
+                tn_cur = __ldg(a.tile_inorm + t_nxt);
+                if (KXT) tcol_cur = __ldg(a.tile_col + t_nxt);
+                if (i + 2 < n_my) t_nxt = tile_of(i + 2);
             }
             const float eb = fmaf(a.cB, tcol, 1e-30f);
             const bool tail = j0 + EPI_COLS > a.N;
@@ -622,8 +711,8 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                     la = la > -INFINITY ? la - fabsf(la) * 2e-6f : la;
                     lb = lb > -INFINITY ? lb - fabsf(lb) * 2e-6f : lb;
                     float* dst = a.cmax + row[mr] * a.n_c;
-                    if (a.cw == 32) *reinterpret_cast<float2*>(dst + (t / a.se) * 4 + h * 2) = make_float2(la, lb);
-                    else dst[(t / a.se) * 2 + h] = fmaxf(la, lb);
+                    if (a.cw == 32) *reinterpret_cast<float2*>(dst + (p_first + i) * 4 + h * 2) = make_float2(la, lb);
+                    else dst[(p_first + i) * 2 + h] = fmaxf(la, lb);
                 } else if (PASS == 1) {
                     const float thr = tl[mr] - E;                     // inf stays inf: no candidates for this row
                     scan_chunk(va, thr, j0, a.N, my_cand[mr], n_local[mr], a.seg_cap);
@@ -715,7 +804,8 @@ __device__ __forceinline__ uint32_t warp_kth_largest(const uint32_t* keys, int n
 
 // one warp per row, n_c keys + 256 histogram bins per warp in dynamic shared memory
 __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restrict__ cmax, int n_c, int n_valid, int64_t M, int64_t M_pad,
-                                                            int se, int cw, const int32_t* __restrict__ users,
+                                                            int se, int cw, const int32_t* __restrict__ tile_pos,
+                                                            const int32_t* __restrict__ users,
                                                             const int64_t* __restrict__ mask_indptr,
                                                             const int32_t* __restrict__ mask_items, int K,
                                                             const int32_t* __restrict__ neg_flag, float* __restrict__ tau) {
@@ -742,7 +832,7 @@ __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restr
     }
     __syncwarp();
     // A sampled chunk that holds ANY train item of this user is dropped: its maximum may belong to a masked item.
-    // chunk c = (sampled tile c / cpt, chunk c % cpt) covers items [(c / cpt) * se * TN + (c % cpt) * cw, + cw)
+    // chunk c = (position c / cpt of the sampled tile list, chunk c % cpt of that tile)
     const int cpt = tc::TN / cw;
     if (mask_indptr) {
         const int u = users[row];
@@ -750,8 +840,9 @@ __global__ void __launch_bounds__(128) tc_tau_select_kernel(const float* __restr
         for (int64_t z = lo + lane; z < hi; z += 32) {
             const int32_t it = __ldg(mask_items + z);
             const int tile = it / tc::TN;
-            if (tile % se == 0) {
-                const int c = (tile / se) * cpt + (it % tc::TN) / cw;
+            const int p = tile_pos ? __ldg(tile_pos + tile) : (tile % se == 0 ? tile / se : -1);     // position in the sampled list
+            if (p >= 0) {
+                const int c = p * cpt + (it % tc::TN) / cw;
                 if (c < n_valid) kk[c] = 0u;
             }
         }
@@ -1210,7 +1301,9 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
         if (want > se) se = want;
     }
     p->cw = cw; p->se = se;
-    p->n_valid = (p->n_tiles + se - 1) / se * (TN / cw);
+    p->n_sel = (p->n_tiles + se - 1) / se;
+    p->ordered = se > 1 && p->n_tiles <= (1 << 20) && env_int("PDA_TC_ORDERED", 1);
+    p->n_valid = p->n_sel * (TN / cw);
     p->n_c = (p->n_valid + 3) / 4 * 4;                        // row stride of cmax: float4 loads in the selection kernel
     // item-range splits: enough CTAs to fill the GPU in whole waves (one CTA per SM: shared memory), equal lengths
     const int m_tiles = (int)(p->M_pad / (TM * MR));
@@ -1249,6 +1342,8 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->o_tcolmax = o; o += al256((size_t)p->n_tiles * 4);
     p->o_targ = o; o += al256((size_t)p->n_tiles * 4);
     p->o_tcol2 = o; o += al256((size_t)p->n_tiles * 4);
+    p->o_torder = o; o += al256((size_t)p->n_tiles * 4);
+    p->o_tpos = o; o += al256((size_t)p->n_tiles * 4);
     p->o_nflag = o; o += 256;          // [0] rows without a certificate, [1] negative-pop flag
     p->o_Ub = o; o += al256((size_t)p->M_pad * a.d * 2);
     p->o_Ux = o; o += al256((size_t)p->M_pad * KX * 2);
@@ -1323,6 +1418,9 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
                                                                                                  (float*)(b + p.o_tcol2));
         else if (kx)
             tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(xcol, p.n_tiles, tcolmax, a.N);
+        if (p.ordered)
+            tc_tile_select_kernel<<<1, 1024, 0, st>>>(tnorm, kx ? tcolmax : nullptr, p.n_tiles, p.n_sel, (int32_t*)(b + p.o_torder),
+                                                      (int32_t*)(b + p.o_tpos));
     }
     tc_convert_rows_kernel<<<(unsigned)((p.M_pad / CONV_RPW * 32 + 255) / 256), 256, 0, st>>>(a.U, a.users, a.M, p.M_pad, a.d, nullptr, nullptr, 1,
                                                                                   Ub, kx ? Ux : nullptr, unorm, nflag + 1);
@@ -1336,6 +1434,8 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
     memset(s, 0, sizeof(*s));
     s->M = a.M; s->N = a.N; s->M_pad = p.M_pad; s->d = a.d; s->kx = kx; s->n_tiles = p.n_tiles;
     s->tiles_per_split = p.tiles_per_split; s->se = p.se;
+    s->n_sel = p.n_sel; s->pos_per_split = (p.n_sel + p.splits - 1) / p.splits;
+    s->order = p.ordered ? (const int32_t*)(b + p.o_torder) : nullptr;
     const float cA = 1.02f / 256.0f + (float)a.d / 2097152.0f, cB = (float)(a.d / 16 + 5) / 524288.0f;
     s->cAB = cA + cB; s->cB = cB;
     s->Ub = Ub; s->Ux = Ux; s->interleave = env_int("PDA_TC_IL", 0);      // measured: no gain (2.89 vs 2.76 ms)
@@ -1370,7 +1470,7 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, bool 
     if (rc) return 10 + rc;
     const size_t tau_smem = (size_t)4 * (p.n_c + 384) * 4;
     if (cudaFuncSetAttribute(tc_tau_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tau_smem) != cudaSuccess) return 15;
-    tc_tau_select_kernel<<<(unsigned)((p.M_pad + 3) / 4), 128, tau_smem, st>>>(s.cmax, p.n_c, p.n_valid, a.M, p.M_pad, p.se, p.cw, a.users,
+    tc_tau_select_kernel<<<(unsigned)((p.M_pad + 3) / 4), 128, tau_smem, st>>>(s.cmax, p.n_c, p.n_valid, a.M, p.M_pad, p.se, p.cw, s.order ? (const int32_t*)(b + p.o_tpos) : nullptr, a.users,
                                                                                a.mask_indptr, a.mask_items, a.K, nflag + 1, tau);
     if (ev) cudaEventRecord(ev[2], st);
     rc = launch_sweep<1>(tm, s, p, m_tiles, st);

@@ -229,3 +229,37 @@ def test_recommend_tensor_extreme_score_scales(pda, c_oracle, scale):
         assert np.array_equal(ids, rid), (rec_type, m.tc_last_stats())
         assert np.array_equal(bits(sc), bits(rsc))
     m.close()
+
+
+@pytest.mark.parametrize("rec_type", ["main_branch", "condition"])
+def test_recommend_tensor_large_item_set_sampled_pass(pda, c_oracle, rec_type, monkeypatch):
+    """> 262144 items: pass A samples a quarter-ish of the tiles -- the ones with the largest item norms / pops
+    (tc_tile_select_kernel) or, PDA_TC_ORDERED=0, every se-th tile.  Same ids and scores either way; the ordered
+    sample must not deliver more candidates than the blind one on popularity-skewed items."""
+    n_users, n_items, d, K = 400, 600000, 64, 50
+    rng = np.random.default_rng(1234)
+    U = (rng.normal(0, 1.0, (n_users, d)) / np.sqrt(d)).astype(np.float32)
+    I = (rng.normal(0, 1.0, (n_items, d)) / np.sqrt(d)).astype(np.float32)
+    I *= (0.2 + rng.random(n_items) ** 4).astype(np.float32)[:, None] * 3.0          # skewed item norms
+    pop = (rng.random(n_items) ** 6).astype(np.float32)
+    from oracle import pda_oracle as po
+    uid, iid, t = synth_interactions(n_users, n_items, 30, 9, seed=9)
+    indptr, items, _ = po.build_csr(n_users, uid, iid, t)
+    m = pda.PDAModel(n_users, n_items, d, train="s_condition", batch_size=64, init=False)
+    m.set_table("user_embedding", U); m.set_table("item_embedding", I)
+    m.set_train_csr(indptr, items)
+    users = np.arange(n_users, dtype=np.int32)
+    rid, rsc = c_oracle.recommend(U, I, users, rec_type, K, indptr, items, pop=pop)
+    cands = {}
+    for ordered in ("1", "0"):
+        monkeypatch.setenv("PDA_TC_ORDERED", ordered)
+        ids, sc = m.do_recommendation(users, None, rec_type, pos_pop=pop, K=K, backend="tensor", return_scores=True)
+        st = m.tc_last_stats()
+        assert st["tile_stride"] > 1, st
+        assert np.array_equal(ids, rid), (ordered, st)
+        assert np.array_equal(bits(sc), bits(rsc))
+        assert st["rows_exact_fallback"] <= 0.05 * n_users, st
+        cands[ordered] = st["candidates"]
+    print("candidates ordered / blind:", cands)
+    assert cands["1"] <= cands["0"] * 1.05
+    m.close()
