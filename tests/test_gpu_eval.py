@@ -251,6 +251,7 @@ def test_recommend_tensor_large_item_set_sampled_pass(pda, c_oracle, rec_type, m
     users = np.arange(n_users, dtype=np.int32)
     rid, rsc = c_oracle.recommend(U, I, users, rec_type, K, indptr, items, pop=pop)
     cands = {}
+    monkeypatch.setenv("PDA_TC_SE", "4")             # the same stride for both samples
     for ordered in ("1", "0"):
         monkeypatch.setenv("PDA_TC_ORDERED", ordered)
         ids, sc = m.do_recommendation(users, None, rec_type, pos_pop=pop, K=K, backend="tensor", return_scores=True)
@@ -262,4 +263,8 @@ def test_recommend_tensor_large_item_set_sampled_pass(pda, c_oracle, rec_type, m
         cands[ordered] = st["candidates"]
     print("candidates ordered / blind:", cands)
     assert cands["1"] <= cands["0"] * 1.05
+    monkeypatch.delenv("PDA_TC_SE")                  # the default stride (8 with the ordered sample)
+    monkeypatch.setenv("PDA_TC_ORDERED", "1")
+    ids = m.do_recommendation(users, None, rec_type, pos_pop=pop, K=K, backend="tensor")
+    assert np.array_equal(ids, rid) and m.tc_last_stats()["tile_stride"] == 8
     m.close()
