@@ -13,15 +13,17 @@
 //                  x_j = pop_j ("condition") or the column bias (BPR(t)-pop) split into three bf16 pieces (24 bits)
 //   accumulator    v_j = sum_k bf(u_k) bf(w_jk) + x_j  ~  (s_j + 1) * pop_j   resp.   s_j + bias_j   resp.   s_j
 //
-//   prep     I, U[users] -> bf16 operands + row norms; per-tile max of |w_j| and |x_j|
-//   pass A   tcgen05 sweep over every `se`-th item tile: per (row, chunk of cw columns) max_j v_j - E, a LOWER bound
+//   prep     I, U[users] -> bf16 operands + row norms; per-tile max of |w_j| and |x_j|; the sample of pass A: all tiles
+//            (<= 131 k items) or the n_tiles / se tiles with the largest max|w_j| + max|x_j| (tc_tile_select_kernel)
+//   pass A   tcgen05 sweep over the sampled item tiles: per (row, chunk of cw columns) max_j v_j - E, a LOWER bound
 //            of the best transformed score of the chunk                                          -> cmax[row][chunk]
 //   select   per row: drop chunks that hold a train item of the user (their maximum may be masked), tau = K-th
 //            largest of the rest.  K distinct unmasked items have exact score >= tau, so the exact K-th best is >= tau.
 //   pass B   tcgen05 sweep over ALL item tiles: items with v_j + E >= tau (UPPER bound reaches tau)  -> cand[row][...]
-//   rescore  per row: exact fp32 score of every candidate, transform, mask, sorted top-K.  The row is CERTIFIED when
-//            the candidate buffer did not overflow and at least K unmasked candidates have exact score >= tau
-//            (then every member of the exact top-K has upper bound >= its score >= K-th best >= tau, i.e. is a candidate).
+//   rescore  collect / score / select kernels: exact fp32 score of every candidate, transform, mask, sorted top-K.  The
+//            row is CERTIFIED when the candidate buffer did not overflow and at least K unmasked candidates have exact
+//            score >= tau (then every member of the exact top-K has upper bound >= its score >= K-th best >= tau,
+//            i.e. is a candidate).
 //   fallback rows that are not certified are recomputed by recommend_exact_kernel (count read on the device, no host sync).
 //
 // Bound.  With acc_j the sequential-k fp32 dot of the spec and y_j the transformed score of the spec:
@@ -37,11 +39,11 @@
 // alone: the rescoring kernel adds those items itself (it scans the tiles whose largest pop reaches the row's tau --
 // none at all once tau > max pop, the fitted-model case).
 //
-// Sweep kernel: one CTA = MR x 128 users resident in shared memory x a range of 128-item tiles.  Warp 0 lane 0
-// issues TMA (128B-swizzled K-major tiles + one 32B-swizzled 16-column tile; A once, B through a ring), warp 1 lane 0
-// issues tcgen05.mma (kind::f16, bf16 -> fp32) into a ring of four 128-column TMEM accumulators, warps 4-11 are the
-// epilogue: tcgen05.ld 32x32b.x32 (a thread = one user row x 64 items), FMNMX3 tree, compare.  The score matrix
-// never leaves TMEM.  Every B tile fetched from L2 serves MR * 128 users.
+// Sweep kernel: one CTA = MR x 128 users resident in shared memory (or tensor memory, TS = 1) x a range of 128-item
+// tiles.  Warps 0-7 are the epilogue: tcgen05.ld 32x32b.x32 (a thread = one user row x 64 items), FMNMX3 tree, compare;
+// warp 8 issues TMA (128B-swizzled K-major tiles + one 32B-swizzled 16-column tile; A once, B through a ring), warp 9
+// issues tcgen05.mma (kind::f16, bf16 -> fp32) into 128-column TMEM accumulators, both through elect.sync.  The score
+// matrix never leaves TMEM.  Every B tile fetched from L2 serves MR * 128 users.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <stdlib.h>
