@@ -209,37 +209,44 @@ def run_ours(a):
         n_e2e = min(a.steps, 10)
         lib = model.lib
         import ctypes as C
-        pinned, batches = [], []
-        for s in range(n_e2e + 2):   # host batches live in pinned memory (cudaHostAlloc through the C ABI)
-            b = model.sample_batch(SEED_SAMPLER + rank, 1, s, B)
-            pb = {}
-            for k in ("users", "pos", "neg", "pos_pop", "neg_pop"):
-                p = lib.pda_host_alloc(b[k].nbytes)
-                arr = np.frombuffer((C.c_byte * b[k].nbytes).from_address(p), dtype=b[k].dtype)
-                arr[:] = b[k]
-                pb[k] = arr
-                pinned.append(p)
-            batches.append(pb)
-        for b in batches[:2]:
-            trainer.train_step_host(b["users"], b["pos"], b["neg"], b["pos_pop"], b["neg_pop"])
-        barrier()
-        t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
-        w0 = time.perf_counter()
-        t0.record()
-        for b in batches[2:]:
-            l3 = trainer.train_step_host(b["users"], b["pos"], b["neg"], b["pos_pop"], b["neg_pop"])
-        t1.record()
-        barrier()
+        keys = ("users", "pos", "neg", "pos_pop", "neg_pop")
+        # host batches live in pinned memory (cudaHostAlloc through the C ABI), [n, B] per array
+        first = model.sample_batch(SEED_SAMPLER + rank, 1, 0, B)
+        pin = {k: model.pinned_array((n_e2e + 2, B), first[k].dtype) for k in keys}
+        for s in range(n_e2e + 2):
+            b = first if s == 0 else model.sample_batch(SEED_SAMPLER + rank, 1, s, B)
+            for k in keys:
+                pin[k][s] = b[k]
+        if world == 1:
+            # the generator-fed epoch loop in one call: batch k+1's copies overlap step k (pda_train_steps_host)
+            model.train_steps(*(pin[k][:2] for k in keys))
+            barrier()
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            t0.record()
+            l3 = model.train_steps(*(pin[k][2:] for k in keys))[-1]
+            t1.record()
+            barrier()
+            api = "PDAModel.train_steps (pda_train_steps_host: n pinned host batches, copies pipelined with the steps)"
+        else:
+            for s in range(2):
+                trainer.train_step_host(*(pin[k][s] for k in keys))
+            barrier()
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            w0 = time.perf_counter()
+            t0.record()
+            for s in range(2, n_e2e + 2):
+                l3 = trainer.train_step_host(*(pin[k][s] for k in keys))
+            t1.record()
+            barrier()
+            api = "ShardedTrainer.train_step_host (pda_stage_batch_host + split step + NCCL exchange)"
         wall = time.perf_counter() - w0
         ems = max(t0.elapsed_time(t1), 0.0)
         te = torch.tensor([max(ems * 1e-3, wall)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = {"value": n_e2e * B * world / float(te.item()), "unit": "triples/s", "h2d_bytes_per_step": 20 * B,
-               "d2h_bytes_per_step": 12, "steps": n_e2e, "api": "PDAModel.train_step (pda_train_step_host)",
-               "last_loss": [float(x) for x in l3]}
-        for p in pinned:
-            lib.pda_host_free(p)
+               "d2h_bytes_per_step": 12, "steps": n_e2e, "api": api, "last_loss": [float(x) for x in l3]}
 
     # ---- eval: all-items scoring + pop adjust + mask + top-50 (pairs/s) ----
     ev = None

@@ -158,6 +158,12 @@ int pda_get_batch(pda_model* m, int64_t B, int32_t* users, int32_t* pos, int32_t
  * device), neg_pop = `raw` (= arange(B); may be NULL, never read). */
 int pda_train_step_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                         const float* pos_pop, const float* neg_pop, int64_t B, float* loss3_out);
+/* n_batches consecutive train steps from PINNED host arrays [n_batches, B] (the generator-fed epoch loop of
+ * train_new_api.py:1078-1098, several sess.run calls at once): batch k+1's host->device copies run on a copy stream
+ * while step k computes.  loss3_out: fp32 [n_batches, 3] = {loss, mf_loss, reg_loss} of every step.  Same results as
+ * n_batches calls of pda_train_step_host. */
+int pda_train_steps_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pos_pop,
+                         const float* neg_pop, int32_t n_batches, int64_t B, float* loss3_out);
 /* device pointers; users == NULL -> use the internal batch written by pda_sample_batch */
 int pda_train_step_device(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                           const float* pos_pop, const float* neg_pop, int64_t B, void* stream);

@@ -55,6 +55,7 @@ PROTOTYPES = {
     "pda_sample_batch": (C.c_int, [c_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64, c_vp]),
     "pda_get_batch": (C.c_int, [c_vp, C.c_int64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "pda_train_step_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp]),
+    "pda_train_steps_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int32, C.c_int64, c_vp]),
     "pda_train_step_device": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp]),
     "pda_train_steps_sampled": (C.c_int, [c_vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int32, C.c_int64, c_vp]),
     "pda_set_global_batch": (C.c_int, [c_vp, C.c_int64]),

@@ -60,6 +60,10 @@ struct pda_model {
     int batch_uniq;   // internal batch holds distinct users (device sampler with B <= #active users)
     int32_t *b_users, *b_pos, *b_neg, *b_time;
     float *b_pp, *b_np;
+    // pda_train_steps_host: second batch slot, copy stream, per-slot events, pinned loss ring
+    int32_t *b2_users, *b2_pos, *b2_neg; float *b2_pp, *b2_np;
+    cudaStream_t copy_st; cudaEvent_t ev_copied[2], ev_stepped[2]; int pipe_ready;
+    float* loss_ring; size_t loss_ring_bytes;
     void* stage_pinned; size_t stage_bytes;
     // eval scratch
     void* ev_buf; size_t ev_bytes;
@@ -201,6 +205,12 @@ void pda_destroy(pda_model* m) {
     cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
     cudaFree(m->pop_train);
     cudaFree(m->b_users); cudaFree(m->b_pos); cudaFree(m->b_neg); cudaFree(m->b_time); cudaFree(m->b_pp); cudaFree(m->b_np);
+    if (m->pipe_ready) {
+        cudaFree(m->b2_users); cudaFree(m->b2_pos); cudaFree(m->b2_neg); cudaFree(m->b2_pp); cudaFree(m->b2_np);
+        cudaStreamDestroy(m->copy_st);
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_stepped[i]); }
+    }
+    if (m->loss_ring) cudaFreeHost(m->loss_ring);
     if (m->stage_pinned) cudaFreeHost(m->stage_pinned);
     if (m->ev_buf) cudaFree(m->ev_buf);
     if (m->tc_buf) cudaFree(m->tc_buf);
@@ -746,7 +756,7 @@ int pda_train_step_host(pda_model* m, const int32_t* users, const int32_t* pos, 
     // anything: check on the device (one pass over B ids, ~50 us at B = 2^20) whether the fused user-row path applies.
     int uniq = 0;
     if (m->adam_lazy[0] && m->fuse_user_adam) {
-        if (!m->seen) { CK(dmalloc(&m->seen, (size_t)m->nU + 1)); CK(cudaMemset(m->seen, 0, ((size_t)m->nU + 1) * 4)); }
+        if (!m->seen) { CK(dmalloc(&m->seen, (size_t)m->nU + 2)); CK(cudaMemset(m->seen, 0, ((size_t)m->nU + 2) * 4)); }
         int32_t* dup = m->seen + m->nU;
         CK(cudaMemsetAsync(dup, 0, 4, 0));
         launch_users_distinct(m->b_users, B, m->seen, ++m->seen_tag, dup, 0);
@@ -761,6 +771,78 @@ int pda_train_step_host(pda_model* m, const int32_t* users, const int32_t* pos, 
     CK(cudaStreamSynchronize(0));
     CK(cudaGetLastError());
     if (loss3_out) memcpy(loss3_out, m->loss3_pinned, 12);
+    return PDA_OK;
+}
+
+// n host batches, pipelined: the H2D copies (+ the distinct-users check) of batch k+1 run on a copy stream while step
+// k computes; two device batch slots, events in both directions, one host wait per batch on the COPY side only.
+int pda_train_steps_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
+                         const float* np_, int32_t n_batches, int64_t B, float* loss3_out) {
+    if (!m || !users || !pos || !neg || n_batches < 1) return fail(PDA_ERR_ARG, "bad argument");
+    if (B < 1 || B > m->cap) return fail(PDA_ERR_ARG, "B=%lld exceeds the batch capacity %lld", (long long)B, (long long)m->cap);
+    if (m->cfg.train_mode == PDA_TRAIN_TEMP_POP) return fail(PDA_ERR_STATE, "pda_train_steps_host covers BPRMF / PD / PDG batches");
+    const bool pop = m->cfg.train_mode == PDA_TRAIN_S_CONDITION;
+    if (pop && (!pp || !np_)) return fail(PDA_ERR_ARG, "s_condition needs pos_pop/neg_pop");
+    CK(cudaSetDevice(m->cfg.device));
+    cudaPointerAttributes at;
+    if (!(cudaPointerGetAttributes(&at, users) == cudaSuccess && at.type == cudaMemoryTypeHost)) {
+        cudaGetLastError();
+        return fail(PDA_ERR_ARG, "pda_train_steps_host needs pinned host batches (pda_host_alloc): pageable memory cannot overlap with compute");
+    }
+    if (!m->pipe_ready) {
+        CK(dmalloc(&m->b2_users, (size_t)m->cap)); CK(dmalloc(&m->b2_pos, (size_t)m->cap)); CK(dmalloc(&m->b2_neg, (size_t)m->cap));
+        CK(dmalloc(&m->b2_pp, (size_t)m->cap)); CK(dmalloc(&m->b2_np, (size_t)m->cap));
+        CK(cudaStreamCreateWithFlags(&m->copy_st, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CK(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&m->ev_stepped[i], cudaEventDisableTiming));
+        }
+        m->pipe_ready = 1;
+    }
+    CK(ensure_pinned((void**)&m->loss_ring, &m->loss_ring_bytes, (size_t)n_batches * 16 + 64));
+    int32_t* hdup = (int32_t*)((char*)m->loss_ring + (size_t)n_batches * 16);      // [2] duplicate flags, one per slot
+    const bool check = m->adam_lazy[0] && m->fuse_user_adam;
+    if (check && !m->seen) { CK(dmalloc(&m->seen, (size_t)m->nU + 2)); CK(cudaMemset(m->seen, 0, ((size_t)m->nU + 2) * 4)); }
+    int32_t* bu[2] = {m->b_users, m->b2_users}; int32_t* bp[2] = {m->b_pos, m->b2_pos}; int32_t* bn[2] = {m->b_neg, m->b2_neg};
+    float* bpp[2] = {m->b_pp, m->b2_pp}; float* bnp[2] = {m->b_np, m->b2_np};
+    const size_t nb = (size_t)B * 4;
+    CK(cudaStreamSynchronize(0));      // everything enqueued before this call is done: both slots are free
+    auto issue_copy = [&](int k) -> cudaError_t {
+        const int sl = k & 1;
+        cudaError_t e;
+        if (k >= 2 && (e = cudaStreamWaitEvent(m->copy_st, m->ev_stepped[sl], 0)) != cudaSuccess) return e;   // step k-2 has read the slot
+        if ((e = cudaMemcpyAsync(bu[sl], users + (size_t)k * B, nb, cudaMemcpyHostToDevice, m->copy_st)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(bp[sl], pos + (size_t)k * B, nb, cudaMemcpyHostToDevice, m->copy_st)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(bn[sl], neg + (size_t)k * B, nb, cudaMemcpyHostToDevice, m->copy_st)) != cudaSuccess) return e;
+        if (pop) {
+            if ((e = cudaMemcpyAsync(bpp[sl], pp + (size_t)k * B, nb, cudaMemcpyHostToDevice, m->copy_st)) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(bnp[sl], np_ + (size_t)k * B, nb, cudaMemcpyHostToDevice, m->copy_st)) != cudaSuccess) return e;
+        }
+        if (check) {      // the reference's batches hold distinct users; a host caller may pass anything (see pda_train_step_host)
+            int32_t* dup = m->seen + m->nU + sl;
+            if ((e = cudaMemsetAsync(dup, 0, 4, m->copy_st)) != cudaSuccess) return e;
+            launch_users_distinct(bu[sl], B, m->seen, ++m->seen_tag, dup, m->copy_st);
+            if ((e = cudaMemcpyAsync(hdup + sl, dup, 4, cudaMemcpyDeviceToHost, m->copy_st)) != cudaSuccess) return e;
+        }
+        return cudaEventRecord(m->ev_copied[sl], m->copy_st);
+    };
+    CK(issue_copy(0));
+    for (int k = 0; k < n_batches; ++k) {
+        const int sl = k & 1;
+        if (k + 1 < n_batches) CK(issue_copy(k + 1));
+        CK(cudaEventSynchronize(m->ev_copied[sl]));            // host: batch k is on the device (step k-1 may still be running)
+        const int uniq = check ? hdup[sl] == 0 : 0;
+        CK(cudaStreamWaitEvent(0, m->ev_copied[sl], 0));
+        m->batch_uniq = 0;
+        int rc = enqueue_step(m, bu[sl], bp[sl], bn[sl], pop ? bpp[sl] : nullptr, pop ? bnp[sl] : nullptr, B, uniq, true, 0);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(m->loss_ring + (size_t)k * 4, m->loss3, 12, cudaMemcpyDeviceToHost, 0));
+        CK(cudaEventRecord(m->ev_stepped[sl], 0));
+    }
+    CK(cudaStreamSynchronize(0));
+    CK(cudaGetLastError());
+    if (loss3_out)
+        for (int k = 0; k < n_batches; ++k) memcpy(loss3_out + (size_t)k * 3, m->loss_ring + (size_t)k * 4, 12);
     return PDA_OK;
 }
 

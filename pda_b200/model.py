@@ -59,6 +59,9 @@ class PDAModel:
         if getattr(self, "_h", None):
             self.lib.pda_destroy(self._h)
             self._h = None
+        for p in getattr(self, "_pinned", []):
+            self.lib.pda_host_free(p)
+        self._pinned = []
 
     def __del__(self):
         try:
@@ -229,6 +232,31 @@ class PDAModel:
     # ---- the step in two halves (data-parallel callers reduce gradients in between) ----
     def set_global_batch(self, Bg):
         check(self.lib.pda_set_global_batch(self._h, int(Bg)))
+
+    def train_steps(self, users, pos_items, neg_items, pos_pop=None, neg_pop=None):
+        """n consecutive train steps from PINNED host arrays of shape [n, B] (allocate them with pinned_array): the
+        host->device copies of batch k+1 overlap step k.  Returns the [n, 3] losses {loss, mf_loss, reg_loss}; the
+        result equals n calls of train_step."""
+        u = np.ascontiguousarray(users, dtype=np.int32)
+        n, B = u.shape
+        p, ng = np.ascontiguousarray(pos_items, dtype=np.int32), np.ascontiguousarray(neg_items, dtype=np.int32)
+        pp = None if pos_pop is None else np.ascontiguousarray(pos_pop, dtype=np.float32)
+        npop = None if neg_pop is None else np.ascontiguousarray(neg_pop, dtype=np.float32)
+        out = np.empty((n, 3), dtype=np.float32)
+        check(self.lib.pda_train_steps_host(self._h, ptr(u), ptr(p), ptr(ng), ptr(pp), ptr(npop), n, B, ptr(out)))
+        return out
+
+    def pinned_array(self, shape, dtype):
+        """numpy view of page-locked host memory (pda_host_alloc); freed with the model"""
+        import ctypes as C
+        dt = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dt.itemsize
+        p = self.lib.pda_host_alloc(nbytes)
+        if not p:
+            raise PdaError("pda_host_alloc failed")
+        self._pinned = getattr(self, "_pinned", [])
+        self._pinned.append(p)
+        return np.frombuffer((C.c_byte * nbytes).from_address(p), dtype=dt).reshape(shape)
 
     def grad_ptr(self, name) -> int:
         return int(self.lib.pda_grad_ptr(self._h, self._TABLES[name]))

@@ -302,3 +302,37 @@ def test_fused_user_adam_in_step_kernel_matches_dense(pda, d):
     assert same.sum() > 0 and np.array_equal(models["lazy"].get_table("user_embedding")[same], U0[same])
     for m in models.values():
         m.close()
+
+
+@pytest.mark.parametrize("adam", ["dense", "lazy"])
+def test_pipelined_host_batches_equal_single_steps(pda, adam):
+    """pda_train_steps_host (copies of batch k+1 overlapped with step k, two device slots) == n calls of
+    pda_train_step_host, bit for bit -- distinct users (fused user-row path when lazy) and one batch with a repeated
+    user in the middle (the device-side check must route that batch through the general path)."""
+    rng = np.random.default_rng(17)
+    n_users, n_items, d, B, n = 3000, 1100, 64, 512, 7
+    U = rng.normal(0, 0.1, (n_users, d)).astype(np.float32)
+    I = rng.normal(0, 0.1, (n_items, d)).astype(np.float32)
+    ms = []
+    for _ in range(2):
+        m = pda.PDAModel(n_users, n_items, d, train="s_condition", batch_size=B, lr=1e-2, regs=1e-3, init=False)
+        m.set_table("user_embedding", U); m.set_table("item_embedding", I)
+        m.set_adam_mode(adam)
+        ms.append(m)
+    a, b = ms
+    users = a.pinned_array((n, B), np.int32); pos = a.pinned_array((n, B), np.int32); neg = a.pinned_array((n, B), np.int32)
+    pp = a.pinned_array((n, B), np.float32); pn = a.pinned_array((n, B), np.float32)
+    for k in range(n):
+        users[k] = rng.permutation(n_users)[:B]
+        perm = rng.permutation(n_items)          # distinct items inside a batch: no atomic-order noise -> bit-exact
+        pos[k], neg[k] = perm[:B], perm[B:2 * B]
+    users[3, 5] = users[3, 4]                    # one batch with a repeated user
+    pp[:] = rng.random((n, B)); pn[:] = rng.random((n, B))
+    got = a.train_steps(users, pos, neg, pp, pn)
+    want = np.asarray([b.train_step(users[k], pos[k], neg[k], pp[k], pn[k]) for k in range(n)], dtype=np.float32)
+    assert np.array_equal(bits(got), bits(want))
+    for t in ("user_embedding", "item_embedding"):
+        assert np.array_equal(bits(a.get_table(t)), bits(b.get_table(t))), t
+    with pytest.raises(pda.PdaError, match="pinned"):
+        a.train_steps(np.array(users), pos, neg, pp, pn)
+    a.close(); b.close()
