@@ -62,7 +62,7 @@ struct pda_model {
     float *b_pp, *b_np;
     // pda_train_steps_host: second batch slot, copy stream, per-slot events, pinned loss ring
     int32_t *b2_users, *b2_pos, *b2_neg; float *b2_pp, *b2_np;
-    cudaStream_t copy_st; cudaEvent_t ev_copied[2], ev_stepped[2]; int pipe_ready;
+    cudaStream_t copy_st; cudaEvent_t ev_copied[2], ev_stepped[2], ev_start; int pipe_ready;
     float* loss_ring; size_t loss_ring_bytes;
     void* stage_pinned; size_t stage_bytes;
     // eval scratch
@@ -209,6 +209,7 @@ void pda_destroy(pda_model* m) {
         cudaFree(m->b2_users); cudaFree(m->b2_pos); cudaFree(m->b2_neg); cudaFree(m->b2_pp); cudaFree(m->b2_np);
         cudaStreamDestroy(m->copy_st);
         for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_stepped[i]); }
+        cudaEventDestroy(m->ev_start);
     }
     if (m->loss_ring) cudaFreeHost(m->loss_ring);
     if (m->stage_pinned) cudaFreeHost(m->stage_pinned);
@@ -475,7 +476,7 @@ int pda_set_train_csr_device(pda_model* m, const int64_t* indptr_d, const int32_
     return PDA_OK;
 }
 
-static int do_sample(pda_model* m, uint32_t seed, uint32_t epoch, uint32_t step, int64_t B, cudaStream_t st) {
+static int do_sample(pda_model* m, uint32_t seed, uint32_t epoch, uint32_t step, int64_t B, cudaStream_t st, int slot = 0) {
     if (!m->indptr) return fail(PDA_ERR_STATE, "pda_set_train_csr has not been called");
     if (m->n_act < 1) return fail(PDA_ERR_STATE, "no user has training data");
     if (B < 1 || B > m->cap) return fail(PDA_ERR_ARG, "B=%lld exceeds the batch capacity %lld", (long long)B, (long long)m->cap);
@@ -492,6 +493,9 @@ static int do_sample(pda_model* m, uint32_t seed, uint32_t epoch, uint32_t step,
     a.pop_train = m->cfg.train_mode == PDA_TRAIN_S_CONDITION ? m->pop_train : nullptr; a.T_pop = m->T_pop;
     a.users_out = m->b_users; a.pos_out = m->b_pos; a.neg_out = m->b_neg; a.time_out = m->b_time;
     a.pos_pop_out = m->b_pp; a.neg_pop_out = m->b_np;
+    if (slot) {      // second batch slot (pipelined callers; BPR(t)-pop never gets here: it needs b_time)
+        a.users_out = m->b2_users; a.pos_out = m->b2_pos; a.neg_out = m->b2_neg; a.pos_pop_out = m->b2_pp; a.neg_pop_out = m->b2_np;
+    }
     { ProfScope ps(m, PDA_PROF_SAMPLER, st); launch_sampler(a, st); }
     m->batch_uniq = B <= m->n_act;
     return PDA_OK;
@@ -774,6 +778,21 @@ int pda_train_step_host(pda_model* m, const int32_t* users, const int32_t* pos, 
     return PDA_OK;
 }
 
+// second batch slot + side stream + events of the pipelined paths (pda_train_steps_host, pda_train_steps_sampled)
+static int ensure_pipe(pda_model* m) {
+    if (m->pipe_ready) return PDA_OK;
+    CK(dmalloc(&m->b2_users, (size_t)m->cap)); CK(dmalloc(&m->b2_pos, (size_t)m->cap)); CK(dmalloc(&m->b2_neg, (size_t)m->cap));
+    CK(dmalloc(&m->b2_pp, (size_t)m->cap)); CK(dmalloc(&m->b2_np, (size_t)m->cap));
+    CK(cudaStreamCreateWithFlags(&m->copy_st, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CK(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&m->ev_stepped[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&m->ev_start, cudaEventDisableTiming));
+    m->pipe_ready = 1;
+    return PDA_OK;
+}
+
 // n host batches, pipelined: the H2D copies (+ the distinct-users check) of batch k+1 run on a copy stream while step
 // k computes; two device batch slots, events in both directions, one host wait per batch on the COPY side only.
 int pda_train_steps_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
@@ -789,16 +808,7 @@ int pda_train_steps_host(pda_model* m, const int32_t* users, const int32_t* pos,
         cudaGetLastError();
         return fail(PDA_ERR_ARG, "pda_train_steps_host needs pinned host batches (pda_host_alloc): pageable memory cannot overlap with compute");
     }
-    if (!m->pipe_ready) {
-        CK(dmalloc(&m->b2_users, (size_t)m->cap)); CK(dmalloc(&m->b2_pos, (size_t)m->cap)); CK(dmalloc(&m->b2_neg, (size_t)m->cap));
-        CK(dmalloc(&m->b2_pp, (size_t)m->cap)); CK(dmalloc(&m->b2_np, (size_t)m->cap));
-        CK(cudaStreamCreateWithFlags(&m->copy_st, cudaStreamNonBlocking));
-        for (int i = 0; i < 2; ++i) {
-            CK(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
-            CK(cudaEventCreateWithFlags(&m->ev_stepped[i], cudaEventDisableTiming));
-        }
-        m->pipe_ready = 1;
-    }
+    { int rc = ensure_pipe(m); if (rc) return rc; }
     CK(ensure_pinned((void**)&m->loss_ring, &m->loss_ring_bytes, (size_t)n_batches * 16 + 64));
     int32_t* hdup = (int32_t*)((char*)m->loss_ring + (size_t)n_batches * 16);      // [2] duplicate flags, one per slot
     const bool check = m->adam_lazy[0] && m->fuse_user_adam;
@@ -851,10 +861,41 @@ int pda_train_steps_sampled(pda_model* m, uint32_t seed, uint32_t epoch, uint32_
     if (!m) return fail(PDA_ERR_ARG, "null model");
     CK(cudaSetDevice(m->cfg.device));
     cudaStream_t st = (cudaStream_t)stream;
+    const bool tmode = m->cfg.train_mode == PDA_TRAIN_TEMP_POP;
+    static const bool overlap = !(getenv("PDA_OVERLAP_SAMPLER") && atoi(getenv("PDA_OVERLAP_SAMPLER")) == 0);
+    if (n_steps >= 2 && !tmode && overlap) {
+        // The sampler of step k+1 depends on nothing step k computes: it runs on a side stream into the other batch slot
+        // while step k's kernels run (latency-bound CSR walks under an HBM-bound Adam sweep).  Slot of step k =
+        // (n_steps-1-k) & 1, so the last batch ends in the primary buffers like in the sequential path.
+        { int rc = ensure_pipe(m); if (rc) return rc; }
+        int32_t* bu[2] = {m->b_users, m->b2_users}; int32_t* bp[2] = {m->b_pos, m->b2_pos}; int32_t* bn[2] = {m->b_neg, m->b2_neg};
+        float* bpp[2] = {m->b_pp, m->b2_pp}; float* bnp[2] = {m->b_np, m->b2_np};
+        CK(cudaEventRecord(m->ev_start, st));                       // both slots are free once the caller's earlier work is done
+        CK(cudaStreamWaitEvent(m->copy_st, m->ev_start, 0));
+        auto slot_of = [&](int k) { return (n_steps - 1 - k) & 1; };
+        int rc = do_sample(m, seed, epoch, step0, B, m->copy_st, slot_of(0));
+        if (rc) return rc;
+        CK(cudaEventRecord(m->ev_copied[slot_of(0)], m->copy_st));
+        for (int32_t k = 0; k < n_steps; ++k) {
+            const int sl = slot_of(k);
+            if (k + 1 < n_steps) {
+                const int sn = slot_of(k + 1);
+                if (k + 1 >= 2) CK(cudaStreamWaitEvent(m->copy_st, m->ev_stepped[sn], 0));     // step k-1 has read that slot
+                rc = do_sample(m, seed, epoch, step0 + (uint32_t)(k + 1), B, m->copy_st, sn);
+                if (rc) return rc;
+                CK(cudaEventRecord(m->ev_copied[sn], m->copy_st));
+            }
+            CK(cudaStreamWaitEvent(st, m->ev_copied[sl], 0));
+            rc = enqueue_step(m, bu[sl], bp[sl], bn[sl], bpp[sl], bnp[sl], B, m->batch_uniq, true, st);
+            if (rc) return rc;
+            CK(cudaEventRecord(m->ev_stepped[sl], st));
+        }
+        CK(cudaGetLastError());
+        return PDA_OK;
+    }
     for (int32_t k = 0; k < n_steps; ++k) {
         int rc = do_sample(m, seed, epoch, step0 + (uint32_t)k, B, st);
         if (rc) return rc;
-        const bool tmode = m->cfg.train_mode == PDA_TRAIN_TEMP_POP;
         rc = enqueue_step(m, m->b_users, m->b_pos, m->b_neg, tmode ? nullptr : m->b_pp, tmode ? nullptr : m->b_np, B,
                           m->batch_uniq, true, st);
         if (rc) return rc;
