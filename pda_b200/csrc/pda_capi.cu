@@ -865,8 +865,9 @@ int pda_train_steps_sampled(pda_model* m, uint32_t seed, uint32_t epoch, uint32_
     static const bool overlap = !(getenv("PDA_OVERLAP_SAMPLER") && atoi(getenv("PDA_OVERLAP_SAMPLER")) == 0);
     if (n_steps >= 2 && !tmode && overlap) {
         // The sampler of step k+1 depends on nothing step k computes: it runs on a side stream into the other batch slot
-        // while step k's kernels run (latency-bound CSR walks under an HBM-bound Adam sweep).  Slot of step k =
-        // (n_steps-1-k) & 1, so the last batch ends in the primary buffers like in the sequential path.
+        // under step k's Adam sweep (latency-bound CSR walks under an HBM-bound sweep) -- it starts when the fused step
+        // kernel of step k is done, so that kernel keeps the GPU to itself.  Slot of step k = (n_steps-1-k) & 1, so the
+        // last batch ends in the primary buffers like in the sequential path.
         { int rc = ensure_pipe(m); if (rc) return rc; }
         int32_t* bu[2] = {m->b_users, m->b2_users}; int32_t* bp[2] = {m->b_pos, m->b2_pos}; int32_t* bn[2] = {m->b_neg, m->b2_neg};
         float* bpp[2] = {m->b_pp, m->b2_pp}; float* bnp[2] = {m->b_np, m->b2_np};
@@ -878,17 +879,20 @@ int pda_train_steps_sampled(pda_model* m, uint32_t seed, uint32_t epoch, uint32_
         CK(cudaEventRecord(m->ev_copied[slot_of(0)], m->copy_st));
         for (int32_t k = 0; k < n_steps; ++k) {
             const int sl = slot_of(k);
+            CK(cudaStreamWaitEvent(st, m->ev_copied[sl], 0));
+            rc = enqueue_fwd_bwd(m, bu[sl], bp[sl], bn[sl], bpp[sl], bnp[sl], B, m->batch_uniq, st, true);
+            if (rc) return rc;
             if (k + 1 < n_steps) {
                 const int sn = slot_of(k + 1);
-                if (k + 1 >= 2) CK(cudaStreamWaitEvent(m->copy_st, m->ev_stepped[sn], 0));     // step k-1 has read that slot
+                // the step kernel of k is done => so is all of step k-1, the last reader of slot sn
+                CK(cudaEventRecord(m->ev_stepped[sl], st));
+                CK(cudaStreamWaitEvent(m->copy_st, m->ev_stepped[sl], 0));
                 rc = do_sample(m, seed, epoch, step0 + (uint32_t)(k + 1), B, m->copy_st, sn);
                 if (rc) return rc;
                 CK(cudaEventRecord(m->ev_copied[sn], m->copy_st));
             }
-            CK(cudaStreamWaitEvent(st, m->ev_copied[sl], 0));
-            rc = enqueue_step(m, bu[sl], bp[sl], bn[sl], bpp[sl], bnp[sl], B, m->batch_uniq, true, st);
+            rc = enqueue_adam(m, true, st);
             if (rc) return rc;
-            CK(cudaEventRecord(m->ev_stepped[sl], st));
         }
         CK(cudaGetLastError());
         return PDA_OK;
