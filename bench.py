@@ -329,8 +329,8 @@ def run_ours(a):
                        "algorithmic_bytes": adam_bytes, "rows_per_step": adam_rows, "mode": a.adam, "unit": "GB/s"},
         "adam_catchup": {"ms_per_step": cat_ms / max(a.steps, 1), "share_of_step": cat_ms / ms,
                          "zero_grad_row_steps_replayed_per_step": row_steps_replayed / max(a.steps, 1)},
-        # the sampler of step k+1 runs on a side stream under step k's kernels: its event pair spans the time it spends
-        # queued behind their CTAs, so its elapsed time is not a share of the step (alone it takes 0.15 ms)
+        # the sampler of step k+1 runs on a side stream under step k's Adam sweep: its event pair spans the time it spends
+        # queued behind that kernel's CTAs, so its elapsed time is not a share of the step (alone it takes 0.15 ms)
         "sampler": {"ms_per_launch": samp_ms / max(samp_n, 1), "concurrent_with_previous_step": world == 1,
                     "share_of_step": None if world == 1 else samp_ms / ms},
     }
