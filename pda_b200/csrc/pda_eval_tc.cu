@@ -396,7 +396,6 @@ struct SweepArgs {
                                // segment = (item split, column half): exactly one owner thread, no atomics
     int32_t* cnt;              // [M_pad][n_seg] entries written (> seg_cap = overflow)
     int n_seg, seg_cap;
-    int interleave;            // shared-memory form: interleave the MMAs of two user tiles
     // pass 2 (diagnostics): the raw accumulators
     float* dense; int64_t dense_ld;
 };
@@ -554,38 +553,6 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             for (int i = 0; i < n_my; ++i) {
                 mbar_wait(bar_full + 8 * s, ph);
                 const uint32_t b_lo = b_lo0 + (uint32_t)s * (b_bytes >> 4);
-                if (!TS && (MR % 2) == 0 && a.interleave) {
-                    // two user tiles at a time, their MMAs interleaved: consecutive instructions then never accumulate
-                    // into the same TMEM tile (back-to-back dependent MMAs leave a bubble in the tensor pipe)
-                    const uint32_t aph = (uint32_t)i & 1u;
-#pragma unroll
-                    for (int mp = 0; mp < MR; mp += 2) {
-                        mbar_wait(bar_tempty + 8 * mp, aph ^ 1u);
-                        mbar_wait(bar_tempty + 8 * (mp + 1), aph ^ 1u);
-                        fence_after();
-                        if (elect_one()) {
-                            const uint32_t d0 = tmem_base + (uint32_t)mp * TN, d1 = d0 + TN;
-                            const uint32_t am0 = a_lo + (uint32_t)mp * (a1_bytes >> 4), am1 = am0 + (a1_bytes >> 4);
-#pragma unroll
-                            for (int kb = 0; kb < KBLK; ++kb)
-#pragma unroll
-                                for (int k = 0; k < KB / 16; ++k) {
-                                    const uint64_t bd = make_desc_hl(DESC_HI_SW128, b_lo + kb * (B_KB_BYTES >> 4) + k * 2);
-                                    umma_bf16(d0, make_desc_hl(DESC_HI_SW128, am0 + kb * (A_KB_BYTES >> 4) + k * 2), bd, IDESC, (kb | k) ? 1u : 0u);
-                                    umma_bf16(d1, make_desc_hl(DESC_HI_SW128, am1 + kb * (A_KB_BYTES >> 4) + k * 2), bd, IDESC, (kb | k) ? 1u : 0u);
-                                }
-                            if (KXT) {
-                                const uint64_t bd = make_desc_hl(DESC_HI_SW32, b_lo + KBLK * (B_KB_BYTES >> 4));
-                                umma_bf16(d0, make_desc_hl(DESC_HI_SW32, am0 + KBLK * (A_KB_BYTES >> 4)), bd, IDESC, 1u);
-                                umma_bf16(d1, make_desc_hl(DESC_HI_SW32, am1 + KBLK * (A_KB_BYTES >> 4)), bd, IDESC, 1u);
-                            }
-                            if (mp == MR - 2) umma_commit(bar_empty + 8 * s);
-                            umma_commit(bar_tfull + 8 * mp);
-                            umma_commit(bar_tfull + 8 * (mp + 1));
-                        }
-                        __syncwarp();
-                    }
-                } else {
 #pragma unroll
                 for (int mr = 0; mr < MR; ++mr) {
                     const int sub = i * MR + mr;
@@ -622,7 +589,6 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                         umma_commit(bar_tfull + 8 * acc);                   // accumulator ready for the epilogue
                     }
                     __syncwarp();
-                }
                 }
                 if (++s == n_stages) { s = 0; ph ^= 1; }
             }
@@ -1444,7 +1410,7 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
     s->order = p.ordered ? (const int32_t*)(b + p.o_torder) : nullptr;
     const float cA = 1.02f / 256.0f + (float)a.d / 2097152.0f, cB = (float)(a.d / 16 + 5) / 524288.0f;
     s->cAB = cA + cB; s->cB = cB;
-    s->Ub = Ub; s->Ux = Ux; s->interleave = env_int("PDA_TC_IL", 0);      // measured: no gain (2.89 vs 2.76 ms)
+    s->Ub = Ub; s->Ux = Ux;
     s->unorm = unorm; s->tile_inorm = tnorm; s->tile_col = kx ? tcolmax : nullptr;
     s->cmax = (float*)(b + p.o_cmax); s->n_c = p.n_c; s->cw = p.cw;
     s->tau = (float*)(b + p.o_tau); s->cand = (int32_t*)(b + p.o_cand); s->cnt = (int32_t*)(b + p.o_cnt);
