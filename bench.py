@@ -207,8 +207,6 @@ def run_ours(a):
     e2e = None
     if not a.no_e2e:
         n_e2e = min(a.steps, 10)
-        lib = model.lib
-        import ctypes as C
         keys = ("users", "pos", "neg", "pos_pop", "neg_pop")
         # host batches live in pinned memory (cudaHostAlloc through the C ABI), [n, B] per array
         first = model.sample_batch(SEED_SAMPLER + rank, 1, 0, B)

@@ -18,13 +18,14 @@ def run(n_users, n_items, d, M, rec_type, deg, reps=5, backends=("exact", "tenso
         m.set_table("user_embedding", m.get_table("user_embedding") * scale)
         m.set_table("item_embedding", m.get_table("item_embedding") * scale)
     degs = np.minimum(1 + rng.poisson(deg, n_users), n_items // 4)
+    if n_users <= 200000:
+        rows = [np.sort(rng.choice(n_items, k, replace=False)) for k in degs]
+    else:
+        draw = np.sort(rng.integers(0, n_items, (n_users, int(degs.max()))), axis=1)
+        rows = [np.unique(draw[u, :degs[u]]) for u in range(n_users)]
     indptr = np.zeros(n_users + 1, dtype=np.int64)
-    indptr[1:] = np.cumsum(degs)
-    items = np.concatenate([np.sort(rng.choice(n_items, k, replace=False)) for k in degs]).astype(np.int32) if n_users <= 200000 else None
-    if items is None:
-        items = np.sort(rng.integers(0, n_items, (n_users, int(degs.max()))), axis=1)
-        items = np.concatenate([np.unique(items[u, :degs[u]]) for u in range(n_users)]).astype(np.int32)
-    m.set_train_csr(indptr if len(items) == indptr[-1] else np.concatenate([[0], np.cumsum(np.diff(indptr))]), items) if len(items) == indptr[-1] else None
+    indptr[1:] = np.cumsum([len(r) for r in rows])
+    m.set_train_csr(indptr, np.concatenate(rows).astype(np.int32))
     pop = (rng.random(n_items) ** 0.22).astype(np.float32)
     users = np.arange(M, dtype=np.int32)
     out = {}
