@@ -222,6 +222,10 @@ int pda_recommend_device(pda_model* m, const int32_t* users, int64_t M, int rec_
  * candidates rescored, max candidates of a row, rows whose candidate list overflowed, pass-A tile stride, sampled
  * chunks per row, item-range splits}.  Synchronises the device. */
 int pda_tc_last_stats(pda_model* m, int64_t* out);
+/* diagnostics, host arithmetic only (no device needed): the launch plan / scratch layout the tensor-core eval would use for
+ * M users x N items: out[24] = {M_pad, N_pad, n_tiles, user tiles per CTA, ts, ordered, n_sel, stride, chunk width, n_c,
+ * n_valid, splits, tiles_per_split, n_seg, seg_cap, rc, total bytes, o_Ib, o_Ub, o_cmax, o_cand, o_clist, o_work, o_nwork} */
+int pda_tc_plan_host(int64_t M, int64_t N, int32_t d, int32_t K, int64_t* out);
 /* diagnostics: the raw tensor-core accumulators the filter compares -- out fp32 [M, n_items]:
  * v[r][j] ~ (u_r . i_j + 1) * pop_j  (PDA_REC_WITH_POP),  u_r . i_j + col_bias_j,  or  u_r . i_j  (bf16 operands, fp32
  * accumulation in TMEM); err_coef[2] = {cAB, cB} of the bound |v - exact| <= cAB |u| |c_j i_j| + cB |x_j|.

@@ -75,6 +75,7 @@ PROTOTYPES = {
     "pda_recommend_device": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_vp, c_vp, C.c_int, C.c_int, C.c_int, c_vp, c_vp,
                                        c_vp]),
     "pda_tc_last_stats": (C.c_int, [c_vp, c_vp]),
+    "pda_tc_plan_host": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, c_vp]),
     "pda_tc_debug_dense_host": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "pda_scores_host": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_vp, c_vp]),
     "pda_metrics_host": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_vp, c_vp, c_vp, C.c_int64, c_vp, C.c_int, c_vp]),

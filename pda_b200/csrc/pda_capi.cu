@@ -1091,6 +1091,22 @@ int pda_tc_last_stats(pda_model* m, int64_t* out) {
     return PDA_OK;
 }
 
+// pure host arithmetic (no CUDA call): the scratch layout / launch plan of the tensor-core eval for a shape
+int pda_tc_plan_host(int64_t M, int64_t N, int32_t d, int32_t K, int64_t* out) {
+    if (!out || M < 1) return fail(PDA_ERR_ARG, "bad argument");
+    EvalArgs a;
+    memset(&a, 0, sizeof(a));
+    a.M = M; a.N = N; a.d = d; a.K = K;
+    if (!tc_supported(a)) return fail(PDA_ERR_ARG, "tensor-core eval needs embed_size in {64,128}, n_items >= 4096, K <= 128");
+    TcPlan p;
+    const size_t total = tc_scratch_bytes(a, &p);
+    const int64_t v[24] = {p.M_pad, p.N_pad, p.n_tiles, p.mr, p.ts, p.ordered, p.n_sel, p.se, p.cw, p.n_c, p.n_valid, p.splits,
+                           p.tiles_per_split, p.n_seg, p.seg_cap, p.rc, (int64_t)total, (int64_t)p.o_Ib, (int64_t)p.o_Ub,
+                           (int64_t)p.o_cmax, (int64_t)p.o_cand, (int64_t)p.o_clist, (int64_t)p.o_work, (int64_t)p.o_nwork};
+    memcpy(out, v, sizeof(v));
+    return PDA_OK;
+}
+
 int pda_tc_debug_dense_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop,
                             const float* col_bias, float* out, float* err_coef) {
     if (!m || !users || !out || M < 1 || M > 32768) return fail(PDA_ERR_ARG, "bad argument");

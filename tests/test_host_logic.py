@@ -236,3 +236,53 @@ def test_early_stop_rule():
         stops.append(stop)
     assert cfg['best_epoch'] == 2 and cfg['best_recall'] == 0.12       # a tie counts as an improvement (>=)
     assert stops == [False, False, False, False, False, True]
+
+
+# ---------------------------------------------------------------------------------------------
+# launch plan of the tensor-core eval (pure host arithmetic of libpda_b200: runs without a GPU)
+# ---------------------------------------------------------------------------------------------
+PLAN_KEYS = ("M_pad", "N_pad", "n_tiles", "mr", "ts", "ordered", "n_sel", "se", "cw", "n_c", "n_valid", "splits",
+             "tiles_per_split", "n_seg", "seg_cap", "rc", "total", "o_Ib", "o_Ub", "o_cmax", "o_cand", "o_clist", "o_work",
+             "o_nwork")
+
+
+def _plan(M, N, d, K=50):
+    import pda_b200
+    from pda_b200._lib import check, ptr
+    out = np.zeros(24, dtype=np.int64)
+    check(pda_b200.load().pda_tc_plan_host(M, N, d, K, ptr(out)))
+    return dict(zip(PLAN_KEYS, (int(x) for x in out)))
+
+
+@pytest.mark.parametrize("N", [4096, 5000, 26047, 128879, 131073, 300000, 1_000_000, 8_000_000])
+@pytest.mark.parametrize("M", [1, 300, 6847, 15974, 32768])
+@pytest.mark.parametrize("d", [64, 128])
+def test_tensor_eval_plan_invariants(M, N, d):
+    p = _plan(M, N, d)
+    rows = 128 * p["mr"]
+    assert p["M_pad"] % rows == 0 and 0 <= p["M_pad"] - M < rows
+    assert p["N_pad"] % 128 == 0 and 0 <= p["N_pad"] - N < 128 and p["n_tiles"] == p["N_pad"] // 128
+    cpt = 128 // p["cw"]
+    assert p["cw"] in (32, 64) and p["se"] >= 1
+    assert p["n_sel"] == -(-p["n_tiles"] // p["se"]) and p["n_valid"] == p["n_sel"] * cpt
+    assert p["n_c"] % 4 == 0 and p["n_valid"] <= p["n_c"] < p["n_valid"] + 4 and p["n_c"] <= 4096 + 3      # keys fit the selection kernel
+    assert (p["se"] == 1) == (p["n_tiles"] * 4 <= 4096) and p["ordered"] == (1 if p["se"] > 1 else 0)
+    assert p["splits"] >= 1 and p["splits"] * p["tiles_per_split"] >= p["n_tiles"] > (p["splits"] - 1) * p["tiles_per_split"]
+    assert p["n_seg"] == 2 * p["splits"] and p["seg_cap"] >= 64 and p["seg_cap"] % 32 == 0
+    assert p["rc"] in (512, 1024, 2048) and p["rc"] // 32 <= 64                                            # work item = row << 6 | round
+    # whole waves of CTAs (one CTA per SM) wherever the item set is long enough to split freely
+    ctas = (p["M_pad"] // rows) * p["splits"]
+    if p["n_tiles"] // p["se"] >= 200 and M >= 6847:
+        assert ctas / 148 / -(-ctas // 148) >= 0.9, ctas
+    offs = [p[k] for k in ("o_Ib", "o_Ub", "o_cmax", "o_cand", "o_clist", "o_work", "o_nwork")]
+    assert offs == sorted(offs) and all(o % 256 == 0 for o in offs) and offs[-1] + 256 == p["total"]
+    assert p["o_Ub"] - p["o_Ib"] >= p["N_pad"] * d * 2                    # item operands first: they outlive a user block
+    assert p["total"] < 16 << 30                                          # per 32768-user block, well inside 180 GB
+
+
+def test_tensor_eval_plan_item_side_is_independent_of_the_user_block():
+    a, b = _plan(32768, 1_000_000, 128), _plan(513, 1_000_000, 128)
+    for k in ("N_pad", "n_tiles", "se", "cw", "n_sel", "n_valid", "o_Ib", "o_Ub"):
+        assert a[k] == b[k], k
+    with pytest.raises(Exception, match="tensor-core eval needs"):
+        _plan(100, 5000, 32)
