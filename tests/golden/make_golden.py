@@ -5,6 +5,9 @@ Run in the build container (where /root/reference exists):  python tests/golden/
   cpp_evaluator.npz         <- evaluator/backend/cpp/include/{evaluate,metric}.h and
                                util/cython/include/arg_topk.h compiled to oracle/_ref/libref_eval.so
   douban_pop_slice.npz      <- data/douban/douban.zip: t_k.txt counts + the shipped item_pop_seq_ori2.txt
+  oracle_step_eval.npz      <- NOT from the reference (its TF1 graph cannot run): the numpy oracle's own output on a
+                               256 x 512 slice (3 PD steps without duplicate items + PD / PDA top-50), SURVEY 8c --
+                               pins the oracle against drift; the C oracle and the CUDA path must reproduce it bit for bit
 The GPU box has no /root/reference; tests only read the committed fixtures.
 """
 import io
@@ -79,7 +82,50 @@ def gen_douban():
     print("douban pop table:", pop.shape, "stage totals", counts.sum(axis=1))
 
 
+def gen_oracle_step_eval():
+    from oracle import pda_oracle as po
+    rng = np.random.default_rng(424242)
+    n_users, n_items, d, B, T, K = 256, 512, 64, 128, 9, 50
+    U0 = po.xavier_init(n_users, d, 2021, 0)
+    I0 = po.xavier_init(n_items, d, 2021, 1)
+    # a little structure so that scores are not all ~0
+    U0 = (U0 + rng.normal(0, 0.3, U0.shape)).astype(np.float32)
+    I0 = (I0 + rng.normal(0, 0.3, I0.shape)).astype(np.float32)
+    pop = rng.random((n_items, T + 1)) ** 2
+    pop[rng.random(pop.shape) < 0.15] = 0.0
+    P = po.train_pop_matrix(pop, 0.22)
+    last, lin = po.eval_pops(pop, 0.22)
+    om = po.OracleModel(n_users, n_items, d, 1e-2, 1e-3, B, "s_condition", U=U0, I=I0)
+    batches, losses = [], []
+    for s in range(3):
+        users = rng.permutation(n_users)[:B].astype(np.int32)          # distinct users (rd.sample)
+        perm = rng.permutation(n_items)
+        pos, neg = perm[:B].astype(np.int32), perm[B:2 * B].astype(np.int32)   # distinct items: fp32 sums have one order
+        t = rng.integers(0, T, B)
+        pp, pn = P[pos, t].astype(np.float32), P[neg, t].astype(np.float32)
+        batches.append((users, pos, neg, pp, pn))
+        losses.append(om.train_step(users, pos, neg, pp, pn))
+    uid = np.repeat(np.arange(n_users), 12)
+    iid = rng.integers(0, n_items, len(uid))
+    key = np.unique(uid.astype(np.int64) * n_items + iid)
+    mptr, mitems, _ = po.build_csr(n_users, key // n_items, key % n_items)
+    eval_users = rng.permutation(n_users)[:200].astype(np.int32)
+    out = dict(U0=U0, I0=I0, U3=om.U, I3=om.I, losses=np.asarray(losses, dtype=np.float32), mask_indptr=mptr, mask_items=mitems,
+               eval_users=eval_users, pop_last=last.astype(np.float32), pop_linear=lin.astype(np.float32), K=K)
+    for s, b in enumerate(batches):
+        for name, arr in zip(("users", "pos", "neg", "pos_pop", "neg_pop"), b):
+            out[f"b{s}_{name}"] = arr
+    for tag, rec, p in (("main", "main_branch", None), ("pda_last", "condition", last), ("pda_linear", "condition", lin)):
+        ids, sc = po.recommend(om.U, om.I, eval_users, rec, K, mptr, mitems, pop=None if p is None else p.astype(np.float32),
+                               return_scores=True)
+        out[f"ids_{tag}"], out[f"scores_{tag}"] = ids.astype(np.int32), sc.astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "oracle_step_eval.npz"), **out)
+    print("oracle step/eval golden:", out["losses"])
+
+
 if __name__ == "__main__":
-    gen_metrics()
-    gen_cpp()
-    gen_douban()
+    if os.path.exists(REF):
+        gen_metrics()
+        gen_cpp()
+        gen_douban()
+    gen_oracle_step_eval()

@@ -336,3 +336,30 @@ def test_pipelined_host_batches_equal_single_steps(pda, adam):
     with pytest.raises(pda.PdaError, match="pinned"):
         a.train_steps(np.array(users), pos, neg, pp, pn)
     a.close(); b.close()
+
+
+def test_cuda_path_reproduces_the_committed_step_and_eval_golden(pda):
+    """tests/golden/oracle_step_eval.npz: 3 PD steps on a 256 x 512 slice + PD / PDA top-50, committed
+    vectors -- no oracle code runs in this test."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_step_eval.npz"))
+    n_users, d = g["U0"].shape
+    n_items = g["I0"].shape[0]
+    B = len(g["b0_users"])
+    for adam in ("dense", "lazy"):
+        m = pda.PDAModel(n_users, n_items, d, train="s_condition", batch_size=B, lr=1e-2, regs=1e-3, init=False)
+        m.set_table("user_embedding", g["U0"]); m.set_table("item_embedding", g["I0"])
+        m.set_adam_mode(adam)
+        for s in range(3):
+            got = m.train_step(*[g[f"b{s}_{k}"] for k in ("users", "pos", "neg", "pos_pop", "neg_pop")])
+            assert np.allclose(got, g["losses"][s], rtol=1e-5, atol=0), (adam, s)
+        assert np.array_equal(bits(m.get_table("user_embedding")), bits(g["U3"])), adam
+        assert np.array_equal(bits(m.get_table("item_embedding")), bits(g["I3"])), adam
+        m.set_train_csr(g["mask_indptr"], g["mask_items"])
+        for tag, rec, p in (("main", "main_branch", None), ("pda_last", "condition", g["pop_last"]),
+                            ("pda_linear", "condition", g["pop_linear"])):
+            ids, sc = m.do_recommendation(g["eval_users"], None, rec, pos_pop=p, K=int(g["K"]), backend="exact",
+                                          return_scores=True)
+            assert np.array_equal(ids, g[f"ids_{tag}"]), (adam, tag)
+            assert np.array_equal(bits(sc), bits(g[f"scores_{tag}"])), (adam, tag)
+        m.close()

@@ -111,3 +111,32 @@ def test_pop_table_formula_reproduces_shipped_douban_table():
     raw = pop[:, -2] + 0.5 * (pop[:, -2] - pop[:, -3])
     assert np.allclose(lin, np.power(np.clip(np.where(raw <= 0, 1e-9, raw), None, 1.0), 0.22).astype(np.float32))
     assert (P == 0).sum() > 1000          # exact zeros survive pop ** gamma
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle-generated golden vectors for the step and the scoring: pins both oracles against drift
+# ---------------------------------------------------------------------------------------------
+def _step_eval_golden():
+    return np.load(os.path.join(GOLD, "oracle_step_eval.npz"))
+
+
+def test_numpy_and_c_oracle_reproduce_the_step_and_eval_golden(c_oracle):
+    from oracle import pda_oracle as po
+    g = _step_eval_golden()
+    B = len(g["b0_users"])
+    om = po.OracleModel(g["U0"].shape[0], g["I0"].shape[0], g["U0"].shape[1], 1e-2, 1e-3, B, "s_condition", U=g["U0"], I=g["I0"])
+    cm = c_oracle.CModel(g["U0"], g["I0"], 1e-2, 1e-3, B, "s_condition")
+    for s in range(3):
+        b = [g[f"b{s}_{k}"] for k in ("users", "pos", "neg", "pos_pop", "neg_pop")]
+        ln, lc = om.train_step(*b), cm.train_step(*b)
+        assert np.array_equal(np.asarray(ln, np.float32).view(np.int32), g["losses"][s].view(np.int32)), s
+        assert np.allclose(lc, g["losses"][s], rtol=1e-6)          # libm logf of the C build: 1e-6, everything else exact
+    for tab, U, I in (("numpy", om.U, om.I), ("c", cm.U, cm.I)):
+        assert np.array_equal(U.view(np.int32), g["U3"].view(np.int32)), tab
+        assert np.array_equal(I.view(np.int32), g["I3"].view(np.int32)), tab
+    K = int(g["K"])
+    for tag, rec, p in (("main", "main_branch", None), ("pda_last", "condition", g["pop_last"]),
+                        ("pda_linear", "condition", g["pop_linear"])):
+        ids, sc = c_oracle.recommend(g["U3"], g["I3"], g["eval_users"], rec, K, g["mask_indptr"], g["mask_items"], pop=p)
+        assert np.array_equal(ids, g[f"ids_{tag}"]), tag
+        assert np.array_equal(sc.view(np.int32), g[f"scores_{tag}"].view(np.int32)), tag
