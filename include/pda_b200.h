@@ -189,8 +189,20 @@ int pda_adam_apply_part(pda_model* m, int part, void* stream);
  * rows [row_lo, row_hi) of one (densely kept) table; after the last range call pda_adam_apply_part(m, 8, stream) --
  * loss / beta-power bookkeeping only */
 int pda_adam_dense_rows(pda_model* m, int which, int64_t row_lo, int64_t row_hi, void* stream);
+/* the same sweep with the gradient of those rows taken from a caller-owned DEVICE buffer grad[row_hi - row_lo, d] (the
+ * output of an out-of-place reduce-scatter); the buffer is left as it is, the model's own accumulator is not touched */
+int pda_adam_dense_rows_ext(pda_model* m, int which, int64_t row_lo, int64_t row_hi, const float* grad, void* stream);
 int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                          const float* pos_pop, const float* neg_pop, int64_t B, void* stream);
+/* pda_stage_batch_host without blocking: the copies and the device-side id check (ids inside their tables, users
+ * distinct) are enqueued on `copy_stream`; pda_staged_batch_wait blocks the HOST until they are done, returns
+ * PDA_ERR_ARG for an id outside its table and makes `stream` wait for the copies.  Lets a data-parallel caller move
+ * batch k+1 while step k's gradient exchange is in flight. */
+int pda_stage_batch_host_async(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
+                               const float* pos_pop, const float* neg_pop, int64_t B, void* copy_stream);
+int pda_staged_batch_wait(pda_model* m, void* stream);
+/* {loss, mf_loss, reg_loss} of the last enqueued step -> PINNED host memory, enqueued on `stream`, no synchronisation */
+int pda_read_loss_async(pda_model* m, float* pinned_dst3, void* stream);
 /* loss3 of the last enqueued step (synchronises `stream`) */
 int pda_read_loss(pda_model* m, float* loss3_out, void* stream);
 /* running sums of the per-step fp32 {loss, mf_loss, reg_loss} in double + the step count since the last

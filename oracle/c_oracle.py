@@ -76,6 +76,12 @@ def num_threads() -> int:
     return int(lib().orc_num_threads())
 
 
+def set_num_threads(n) -> int:
+    """OpenMP team size of every later call (bench.py: all host cores, whatever OMP_NUM_THREADS the launcher exported)."""
+    lib().orc_set_num_threads(C.c_int(int(n)))
+    return num_threads()
+
+
 def xavier_init(rows, cols, seed, table_id):
     W = np.empty((rows, cols), dtype=np.float32)
     lib().orc_xavier_init(_p(W, c_f), C.c_int64(rows), C.c_int(cols), C.c_uint32(seed), C.c_uint32(table_id))

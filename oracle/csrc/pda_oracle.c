@@ -52,6 +52,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* bench.py's reference arm: use every host core even when the launcher exported OMP_NUM_THREADS=1 (torchrun does) */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 static inline uint32_t mulhi(uint32_t r, uint32_t n) { return (uint32_t)(((uint64_t)r * n) >> 32); }
 
 /* ---- a1: Xavier init (MF/model_api.py:86-99) ---- */

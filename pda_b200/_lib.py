@@ -66,6 +66,10 @@ PROTOTYPES = {
     "pda_adam_apply_part": (C.c_int, [c_vp, C.c_int, c_vp]),
     "pda_adam_dense_rows": (C.c_int, [c_vp, C.c_int, C.c_int64, C.c_int64, c_vp]),
     "pda_stage_batch_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp]),
+    "pda_stage_batch_host_async": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp]),
+    "pda_staged_batch_wait": (C.c_int, [c_vp, c_vp]),
+    "pda_read_loss_async": (C.c_int, [c_vp, c_vp, c_vp]),
+    "pda_adam_dense_rows_ext": (C.c_int, [c_vp, C.c_int, C.c_int64, C.c_int64, c_vp, c_vp]),
     "pda_read_loss": (C.c_int, [c_vp, c_vp, c_vp]),
     "pda_read_loss_sums": (C.c_int, [c_vp, c_vp, C.c_int, c_vp]),
     "pda_gradients_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp, c_vp, c_vp]),

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(256, 6) adam_lazy_rows_kernel(LazyArgs a) {
     const int q = a.d >> 2;
     const int64_t t = a.step_no;
     const int32_t claim = (int32_t)(2 * (t + 1) + PHASE);
+    const bool lr_ok = lr_in_replay_range(a.lr);
     float lr_t = 0.f;
     if (PHASE == 1) {
         const float b1p = a.pw[0], b2p = a.pw[1];
@@ -58,7 +59,12 @@ __global__ void __launch_bounds__(256, 6) adam_lazy_rows_kernel(LazyArgs a) {
         const bool mine = lazy_tbl && old != claim;
         if (!mine) continue;
         int32_t* ap = a.applied[tbl] + row;
-        const int64_t done = *ap;
+        // read by the group's first lane only and broadcast: that lane rewrites applied[row] below, and lanes of a
+        // group are not guaranteed to stay in lockstep through the replay
+        int32_t done32 = 0;
+        if (gl == 0) done32 = *ap;
+        const uint32_t gmask = G == 32 ? 0xffffffffu : ((1u << G) - 1u) << (gw * G);   // `mine` is uniform within a group
+        const int64_t done = __shfl_sync(gmask, done32, gw * G);
         float* Wr = a.W[tbl] + row * a.d;
         float* Mr = a.m[tbl] + row * a.d;
         float* Vr = a.v[tbl] + row * a.d;
@@ -71,7 +77,7 @@ __global__ void __launch_bounds__(256, 6) adam_lazy_rows_kernel(LazyArgs a) {
                     if (ch < q) {
                         float4 w = *reinterpret_cast<float4*>(Wr + 4 * ch), m = *reinterpret_cast<float4*>(Mr + 4 * ch),
                                v = *reinterpret_cast<float4*>(Vr + 4 * ch);
-                        lazy_replay4(w, m, v, a.lr_hist, done, t);
+                        lazy_replay4_blocked(w, m, v, a.lr_hist, done, t, lr_ok);
                         *reinterpret_cast<float4*>(Wr + 4 * ch) = w;
                         *reinterpret_cast<float4*>(Mr + 4 * ch) = m;
                         *reinterpret_cast<float4*>(Vr + 4 * ch) = v;
@@ -145,6 +151,7 @@ __global__ void __launch_bounds__(256) adam_lazy_flush_kernel(LazyArgs a, int tb
     const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     const int q = a.d >> 2;
     const int64_t t = a.step_no;
+    const bool lr_ok = lr_in_replay_range(a.lr);
     for (int64_t row = warp_global; row < n_rows; row += n_warps) {
         int32_t* ap = a.applied[tbl] + row;
         const int64_t done = *ap;
@@ -156,7 +163,7 @@ __global__ void __launch_bounds__(256) adam_lazy_flush_kernel(LazyArgs a, int tb
             for (int ch = lane; ch < q; ch += 32) {
                 float4 w = *reinterpret_cast<float4*>(Wr + 4 * ch), m = *reinterpret_cast<float4*>(Mr + 4 * ch),
                        v = *reinterpret_cast<float4*>(Vr + 4 * ch);
-                lazy_replay4(w, m, v, a.lr_hist, done, t);
+                lazy_replay4_blocked(w, m, v, a.lr_hist, done, t, lr_ok);
                 *reinterpret_cast<float4*>(Wr + 4 * ch) = w;
                 *reinterpret_cast<float4*>(Mr + 4 * ch) = m;
                 *reinterpret_cast<float4*>(Vr + 4 * ch) = v;

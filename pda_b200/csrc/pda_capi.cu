@@ -45,6 +45,10 @@ struct pda_model {
     const int32_t *cur_users, *cur_pos, *cur_neg; int64_t cur_B;   // batch of the step in flight
     int cur_fused, fuse_user_adam;
     int32_t* seen; int32_t seen_tag;   // scratch of the distinct-users check of host batches
+    int32_t* chk_flags;                // device {users repeat, id out of range} x 2 slots (+ the asynchronous staging slot)
+    int32_t* chk_pinned;               // pinned mirror of chk_flags
+    cudaEvent_t ev_staged; int staged_pending;   // pda_stage_batch_host_async / pda_staged_batch_wait
+    int32_t max_time;                  // largest stage label of the host-validated train CSR (-1: unknown)
     float* pw;          // {beta1_power, beta2_power}
     double* loss_acc;   // {sum log(sigmoid+1e-10), sum of squares}
     float* loss3;       // device {loss, mf, reg}
@@ -187,6 +191,10 @@ int pda_create(const pda_config* cfg, pda_model** out) {
     CK(cudaMemcpy(m->pw, pw0, 8, cudaMemcpyHostToDevice));
     CK(cudaMemset(m->loss_acc, 0, 16)); CK(cudaMemset(m->loss3, 0, 16)); CK(cudaMemset(m->loss_sum, 0, 32));
     CK(cudaHostAlloc((void**)&m->loss3_pinned, 64, cudaHostAllocDefault));
+    CK(dmalloc(&m->chk_flags, 8)); CK(cudaMemset(m->chk_flags, 0, 32));   // 3 slots x {repeat, bad id} (+ pad)
+    CK(cudaHostAlloc((void**)&m->chk_pinned, 32, cudaHostAllocDefault));
+    CK(cudaEventCreateWithFlags(&m->ev_staged, cudaEventDisableTiming));
+    m->max_time = -1;
     CK(dmalloc(&m->b_users, (size_t)m->cap)); CK(dmalloc(&m->b_pos, (size_t)m->cap)); CK(dmalloc(&m->b_neg, (size_t)m->cap));
     CK(dmalloc(&m->b_time, (size_t)m->cap)); CK(dmalloc(&m->b_pp, (size_t)m->cap)); CK(dmalloc(&m->b_np, (size_t)m->cap));
     CK(cudaDeviceSynchronize());
@@ -200,7 +208,8 @@ void pda_destroy(pda_model* m) {
     cudaDeviceSynchronize();
     for (int t = 0; t < 4; ++t) { cudaFree(m->W[t]); cudaFree(m->Mo[t]); cudaFree(m->Vo[t]); cudaFree(m->G[t]); }
     for (int t = 0; t < 2; ++t) { cudaFree(m->applied[t]); cudaFree(m->stamp[t]); }
-    cudaFree(m->lr_hist); cudaFree(m->lazy_stats); cudaFree(m->seen);
+    cudaFree(m->lr_hist); cudaFree(m->lazy_stats); cudaFree(m->seen); cudaFree(m->chk_flags);
+    cudaFreeHost(m->chk_pinned); cudaEventDestroy(m->ev_staged);
     cudaFree(m->pw); cudaFree(m->loss_acc); cudaFree(m->loss3); cudaFree(m->loss_sum); cudaFreeHost(m->loss3_pinned);
     cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
     cudaFree(m->pop_train);
@@ -413,6 +422,13 @@ int pda_set_train_csr(pda_model* m, const int64_t* indptr, const int32_t* items,
     }
     for (int64_t q = 0; q < nnz; ++q)
         if (items[q] < 0 || items[q] >= m->nI) return fail(PDA_ERR_ARG, "item id out of range at %lld", (long long)q);
+    int32_t max_time = -1;
+    if (times) for (int64_t q = 0; q < nnz; ++q) if ((int32_t)times[q] > max_time) max_time = times[q];
+    if (unique_times) for (int32_t q = 0; q < n_times; ++q) if (unique_times[q] > max_time) max_time = unique_times[q];
+    if (m->pop_train && m->T_pop > 1 && max_time >= m->T_pop)
+        return fail(PDA_ERR_ARG, "stage label %d has no column in the popularity table (T_pop = %d)", max_time, m->T_pop);
+    if (m->cfg.train_mode == PDA_TRAIN_TEMP_POP && max_time >= m->cfg.temp_num)
+        return fail(PDA_ERR_ARG, "stage label %d outside the temp_num = %d train stages", max_time, m->cfg.temp_num);
     cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
     m->indptr = nullptr; m->items = nullptr; m->times = nullptr; m->active = nullptr; m->unique_times = nullptr;
     CK(dmalloc(&m->indptr, (size_t)m->nU + 1));
@@ -431,7 +447,7 @@ int pda_set_train_csr(pda_model* m, const int64_t* indptr, const int32_t* items,
     CK(dmalloc(&m->active, (size_t)n_act));
     if (n_act) CK(cudaMemcpy(m->active, act, (size_t)n_act * 4, cudaMemcpyHostToDevice));
     free(act);
-    m->n_act = n_act; m->nnz = nnz;
+    m->n_act = n_act; m->nnz = nnz; m->max_time = max_time;
     m->n_times = 0;
     if (unique_times && n_times > 0) {
         CK(dmalloc(&m->unique_times, (size_t)n_times));
@@ -443,6 +459,10 @@ int pda_set_train_csr(pda_model* m, const int64_t* indptr, const int32_t* items,
 
 int pda_set_train_pop(pda_model* m, const float* pop, int32_t T_pop) {
     if (!m || !pop || T_pop < 1) return fail(PDA_ERR_ARG, "bad argument");
+    // the sampler reads pop[item, stage]: every stage label of the train CSR needs a column (the reference's numpy
+    // lookup raises IndexError otherwise, train_new_api.py:402-403)
+    if (T_pop > 1 && m->max_time >= T_pop)
+        return fail(PDA_ERR_ARG, "stage label %d has no column in the popularity table (T_pop = %d)", m->max_time, T_pop);
     CK(cudaSetDevice(m->cfg.device));
     cudaFree(m->pop_train); m->pop_train = nullptr;
     CK(dmalloc(&m->pop_train, (size_t)m->nI * T_pop));
@@ -467,7 +487,7 @@ int pda_set_train_csr_device(pda_model* m, const int64_t* indptr_d, const int32_
         CK(dmalloc(&m->times, (size_t)nnz));
         CK(cudaMemcpy(m->times, times_d, (size_t)nnz, cudaMemcpyDeviceToDevice));
     }
-    m->n_act = n_act; m->nnz = nnz; m->n_times = 0;
+    m->n_act = n_act; m->nnz = nnz; m->n_times = 0; m->max_time = -1;   // device arrays are taken as they are
     if (unique_times && n_times > 0) {
         CK(dmalloc(&m->unique_times, (size_t)n_times));
         CK(cudaMemcpy(m->unique_times, unique_times, (size_t)n_times * 4, cudaMemcpyHostToDevice));
@@ -670,6 +690,24 @@ int pda_adam_dense_rows(pda_model* m, int which, int64_t row_lo, int64_t row_hi,
     return PDA_OK;
 }
 
+int pda_adam_dense_rows_ext(pda_model* m, int which, int64_t row_lo, int64_t row_hi, const float* grad, void* stream) {
+    if (!m || !grad || (which != PDA_TABLE_USER && which != PDA_TABLE_ITEM)) return fail(PDA_ERR_ARG, "bad argument");
+    const int t = which == PDA_TABLE_USER ? 0 : 1;
+    if (row_lo < 0 || row_hi > m->rows[t] || row_lo > row_hi) return fail(PDA_ERR_ARG, "row range outside the table");
+    if (m->adam_lazy[t]) return fail(PDA_ERR_STATE, "the table is kept lazily: there is no dense sweep to run on it");
+    if (row_lo == row_hi) return PDA_OK;
+    CK(cudaSetDevice(m->cfg.device));
+    AdamArgs a;
+    memset(&a, 0, sizeof(a));
+    const size_t off = (size_t)row_lo * m->d;
+    a.W[0] = m->W[t] + off; a.m[0] = m->Mo[t] + off; a.v[0] = m->Vo[t] + off; a.G[0] = const_cast<float*>(grad);
+    a.n4[0] = (row_hi - row_lo) * m->d / 4;
+    a.pw = m->pw; a.lr = m->cfg.lr; a.keep_g = 1;
+    { ProfScope ps(m, PDA_PROF_ADAM, (cudaStream_t)stream); launch_adam_dense(a, (cudaStream_t)stream); }
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
 int pda_adam_apply_part(pda_model* m, int part, void* stream) {
     if (!m || (part != 1 && part != 2 && part != 3 && part != 8)) return fail(PDA_ERR_ARG, "bad argument");
     CK(cudaSetDevice(m->cfg.device));
@@ -707,6 +745,17 @@ int pda_train_step_device(pda_model* m, const int32_t* users, const int32_t* pos
     int rc = enqueue_step(m, users, pos, neg, pp, np_, B, uniq, true, (cudaStream_t)stream);
     if (rc) return rc;
     CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+// enqueue the id check of a device batch on `st`: flags land in chk_pinned[2*slot] (users repeat) and [2*slot+1] (bad id)
+static int check_batch(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, int64_t B, bool want_uniq,
+                       int slot, cudaStream_t st) {
+    if (want_uniq && !m->seen) { CK(dmalloc(&m->seen, (size_t)m->nU)); CK(cudaMemset(m->seen, 0, (size_t)m->nU * 4)); }
+    int32_t* fl = m->chk_flags + 2 * slot;
+    CK(cudaMemsetAsync(fl, 0, 8, st));
+    launch_batch_check(users, pos, neg, B, (int32_t)m->nU, (int32_t)m->nI, want_uniq ? m->seen : nullptr, ++m->seen_tag, fl, st);
+    CK(cudaMemcpyAsync(m->chk_pinned + 2 * slot, fl, 8, cudaMemcpyDeviceToHost, st));
     return PDA_OK;
 }
 
@@ -750,24 +799,61 @@ int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos,
     return stage_batch(m, users, pos, neg, pp, np_, B, (cudaStream_t)stream);
 }
 
+// pda_stage_batch_host for callers that overlap the copies with device work (data-parallel host-batch loops): copies +
+// the id / distinct-users check are enqueued on `copy_stream` and the call returns; pda_staged_batch_wait blocks the
+// HOST until they are done (nothing else), validates, and makes `stream` wait for them.
+int pda_stage_batch_host_async(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg, const float* pp,
+                               const float* np_, int64_t B, void* copy_stream) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    CK(cudaSetDevice(m->cfg.device));
+    cudaStream_t cs = (cudaStream_t)copy_stream;
+    int rc = stage_batch(m, users, pos, neg, pp, np_, B, cs);
+    if (rc) return rc;
+    rc = check_batch(m, m->b_users, m->b_pos, m->b_neg, B, m->adam_lazy[0] && m->fuse_user_adam, 2, cs);
+    if (rc) return rc;
+    CK(cudaEventRecord(m->ev_staged, cs));
+    m->staged_pending = 1;
+    return PDA_OK;
+}
+
+int pda_staged_batch_wait(pda_model* m, void* stream) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    if (!m->staged_pending) return fail(PDA_ERR_STATE, "no batch was staged with pda_stage_batch_host_async");
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaEventSynchronize(m->ev_staged));
+    CK(cudaStreamWaitEvent((cudaStream_t)stream, m->ev_staged, 0));
+    m->staged_pending = 0;
+    if (m->chk_pinned[5]) return fail(PDA_ERR_ARG, "batch holds a user / item id outside [0, n_users) / [0, n_items)");
+    m->batch_uniq = (m->adam_lazy[0] && m->fuse_user_adam && m->chk_pinned[4] == 0) ? 1 : 0;
+    return PDA_OK;
+}
+
+// {loss, mf_loss, reg_loss} of the last enqueued step -> pinned host memory, enqueued on `stream` (no synchronisation:
+// the caller reads it after its own sync)
+int pda_read_loss_async(pda_model* m, float* pinned_dst3, void* stream) {
+    if (!m || !pinned_dst3) return fail(PDA_ERR_ARG, "null argument");
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaMemcpyAsync(pinned_dst3, m->loss3, 12, cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    return PDA_OK;
+}
+
 int pda_train_step_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                         const float* pp, const float* np_, int64_t B, float* loss3_out) {
     if (!m) return fail(PDA_ERR_ARG, "null model");
     CK(cudaSetDevice(m->cfg.device));
     int rc = stage_batch(m, users, pos, neg, pp, np_, B, 0);
     if (rc) return rc;
-    // The reference's batches hold distinct users (rd.sample, train_new_api.py:384-385) but a host caller may pass
-    // anything: check on the device (one pass over B ids, ~50 us at B = 2^20) whether the fused user-row path applies.
+    // One pass over the ids on the device (~50 us at B = 2^20): ids outside their table are an error (the reference's
+    // embedding_lookup raises), and the fused user-row path applies only when the users are distinct -- the reference's
+    // batches are (rd.sample, train_new_api.py:384-385) but a host caller may pass anything.
     int uniq = 0;
-    if (m->adam_lazy[0] && m->fuse_user_adam) {
-        if (!m->seen) { CK(dmalloc(&m->seen, (size_t)m->nU + 2)); CK(cudaMemset(m->seen, 0, ((size_t)m->nU + 2) * 4)); }
-        int32_t* dup = m->seen + m->nU;
-        CK(cudaMemsetAsync(dup, 0, 4, 0));
-        launch_users_distinct(m->b_users, B, m->seen, ++m->seen_tag, dup, 0);
-        int32_t* hdup = (int32_t*)((char*)m->loss3_pinned + 56);
-        CK(cudaMemcpyAsync(hdup, dup, 4, cudaMemcpyDeviceToHost, 0));
+    {
+        const bool want_uniq = m->adam_lazy[0] && m->fuse_user_adam;
+        int rc2 = check_batch(m, m->b_users, m->b_pos, m->b_neg, B, want_uniq, 0, 0);
+        if (rc2) return rc2;
         CK(cudaStreamSynchronize(0));
-        uniq = *hdup == 0;
+        if (m->chk_pinned[1]) return fail(PDA_ERR_ARG, "batch holds a user / item id outside [0, n_users) / [0, n_items)");
+        uniq = want_uniq && m->chk_pinned[0] == 0;
     }
     rc = enqueue_step(m, m->b_users, m->b_pos, m->b_neg, m->b_pp, m->b_np, B, uniq, true, 0);
     if (rc) return rc;
@@ -810,9 +896,7 @@ int pda_train_steps_host(pda_model* m, const int32_t* users, const int32_t* pos,
     }
     { int rc = ensure_pipe(m); if (rc) return rc; }
     CK(ensure_pinned((void**)&m->loss_ring, &m->loss_ring_bytes, (size_t)n_batches * 16 + 64));
-    int32_t* hdup = (int32_t*)((char*)m->loss_ring + (size_t)n_batches * 16);      // [2] duplicate flags, one per slot
     const bool check = m->adam_lazy[0] && m->fuse_user_adam;
-    if (check && !m->seen) { CK(dmalloc(&m->seen, (size_t)m->nU + 2)); CK(cudaMemset(m->seen, 0, ((size_t)m->nU + 2) * 4)); }
     int32_t* bu[2] = {m->b_users, m->b2_users}; int32_t* bp[2] = {m->b_pos, m->b2_pos}; int32_t* bn[2] = {m->b_neg, m->b2_neg};
     float* bpp[2] = {m->b_pp, m->b2_pp}; float* bnp[2] = {m->b_np, m->b2_np};
     const size_t nb = (size_t)B * 4;
@@ -828,12 +912,8 @@ int pda_train_steps_host(pda_model* m, const int32_t* users, const int32_t* pos,
             if ((e = cudaMemcpyAsync(bpp[sl], pp + (size_t)k * B, nb, cudaMemcpyHostToDevice, m->copy_st)) != cudaSuccess) return e;
             if ((e = cudaMemcpyAsync(bnp[sl], np_ + (size_t)k * B, nb, cudaMemcpyHostToDevice, m->copy_st)) != cudaSuccess) return e;
         }
-        if (check) {      // the reference's batches hold distinct users; a host caller may pass anything (see pda_train_step_host)
-            int32_t* dup = m->seen + m->nU + sl;
-            if ((e = cudaMemsetAsync(dup, 0, 4, m->copy_st)) != cudaSuccess) return e;
-            launch_users_distinct(bu[sl], B, m->seen, ++m->seen_tag, dup, m->copy_st);
-            if ((e = cudaMemcpyAsync(hdup + sl, dup, 4, cudaMemcpyDeviceToHost, m->copy_st)) != cudaSuccess) return e;
-        }
+        // id range + distinct users, on the copy stream (see pda_train_step_host)
+        if (check_batch(m, bu[sl], bp[sl], bn[sl], B, check, sl, m->copy_st)) return cudaErrorUnknown;
         return cudaEventRecord(m->ev_copied[sl], m->copy_st);
     };
     CK(issue_copy(0));
@@ -841,7 +921,11 @@ int pda_train_steps_host(pda_model* m, const int32_t* users, const int32_t* pos,
         const int sl = k & 1;
         if (k + 1 < n_batches) CK(issue_copy(k + 1));
         CK(cudaEventSynchronize(m->ev_copied[sl]));            // host: batch k is on the device (step k-1 may still be running)
-        const int uniq = check ? hdup[sl] == 0 : 0;
+        if (m->chk_pinned[2 * sl + 1]) {
+            cudaDeviceSynchronize();
+            return fail(PDA_ERR_ARG, "batch %d holds a user / item id outside [0, n_users) / [0, n_items)", k);
+        }
+        const int uniq = check ? m->chk_pinned[2 * sl] == 0 : 0;
         CK(cudaStreamWaitEvent(0, m->ev_copied[sl], 0));
         m->batch_uniq = 0;
         int rc = enqueue_step(m, bu[sl], bp[sl], bn[sl], pop ? bpp[sl] : nullptr, pop ? bnp[sl] : nullptr, B, uniq, true, 0);
@@ -936,6 +1020,10 @@ int pda_gradients_host(pda_model* m, const int32_t* users, const int32_t* pos, c
     CK(cudaSetDevice(m->cfg.device));
     int rc = stage_batch(m, users, pos, neg, pp, np_, B, 0);
     if (rc) return rc;
+    rc = check_batch(m, m->b_users, m->b_pos, m->b_neg, B, false, 0, 0);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(0));
+    if (m->chk_pinned[1]) return fail(PDA_ERR_ARG, "batch holds a user / item id outside [0, n_users) / [0, n_items)");
     rc = enqueue_step(m, m->b_users, m->b_pos, m->b_neg, m->b_pp, m->b_np, B, 0, false, 0);
     if (rc) return rc;
     CK(cudaStreamSynchronize(0));
@@ -1042,6 +1130,8 @@ int pda_recommend_device(pda_model* m, const int32_t* users, int64_t M, int rec_
 int pda_recommend_host(pda_model* m, const int32_t* users, int64_t M, int rec_type, const float* pop,
                        const float* col_bias, int use_mask, int K, int backend, int32_t* ids_out, float* scores_out) {
     if (!m || !users || !ids_out || M < 1 || K < 1) return fail(PDA_ERR_ARG, "bad argument");
+    for (int64_t r = 0; r < M; ++r)
+        if (users[r] < 0 || users[r] >= m->nU) return fail(PDA_ERR_ARG, "user id %d outside [0, n_users) at position %lld", users[r], (long long)r);
     CK(cudaSetDevice(m->cfg.device));
     const size_t nu = ((size_t)M * 4 + 255) / 256 * 256, nv = ((size_t)m->nI * 4 + 255) / 256 * 256;
     const size_t nk = ((size_t)M * K * 4 + 255) / 256 * 256;
@@ -1175,6 +1265,9 @@ int pda_metrics_host(pda_model* m, const int32_t* ids, int64_t M, int Kkeep, con
                      int nK, double* out) {
     if (!m || !ids || !eval_users || !truth_indptr || !Ks || !out || M < 1 || nK < 1 || nK > 16)
         return fail(PDA_ERR_ARG, "bad argument");
+    for (int64_t r = 0; r < M; ++r)
+        if (eval_users[r] < 0 || eval_users[r] >= n_truth_rows)
+            return fail(PDA_ERR_ARG, "eval user id %d outside the truth CSR at position %lld", eval_users[r], (long long)r);
     CK(cudaSetDevice(m->cfg.device));
     const int64_t nnz = truth_indptr[n_truth_rows];
     auto al = [](size_t x) { return (x + 255) / 256 * 256; };

@@ -41,6 +41,7 @@ struct AdamArgs {
     int64_t n4[4];       // float4 count of each array (0 = unused)
     const float* pw;     // {beta1_power, beta2_power}
     float lr;
+    int keep_g;          // 1: leave G as it is (an exchange buffer the caller owns) instead of zeroing it
 };
 
 // exact lazy replay of the dense Adam sweep (pda_adam_lazy.cu)
@@ -79,12 +80,14 @@ void launch_xavier_init(float* W, int64_t rows, int cols, uint32_t seed, uint32_
 void sampler_keys(uint32_t seed, uint32_t epoch, uint32_t step, uint32_t* keys);
 void launch_sampler(SamplerArgs a, cudaStream_t st);
 int launch_bpr_step(const StepArgs& a, cudaStream_t st);
+int launch_bpr_step_pipe(const StepArgs& a, cudaStream_t st);   // pda_step_pipe.cu; non-zero = shape not covered
 void launch_adam_dense(const AdamArgs& a, cudaStream_t st);
 void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float* pw, int64_t B, float regs,
                         int batch_size, int advance_powers, float lr, float* lr_slot, cudaStream_t st);
 int launch_adam_lazy_rows(const LazyArgs& a, int phase, cudaStream_t st);
 void launch_adam_lazy_flush(const LazyArgs& a, int tbl, int64_t n_rows, cudaStream_t st);
-void launch_users_distinct(const int32_t* users, int64_t B, int32_t* seen, int32_t tag, int32_t* dup, cudaStream_t st);
+void launch_batch_check(const int32_t* users, const int32_t* pos, const int32_t* neg, int64_t B, int32_t n_users,
+                        int32_t n_items, int32_t* seen, int32_t tag, int32_t* flags, cudaStream_t st);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t value, cudaStream_t st);
 void launch_f32_to_i32(const float* src, int32_t* dst, int64_t n, int32_t max_value, cudaStream_t st);
 void launch_temp_item_bias(const float* ub, const float* ib, int64_t n_items, int temp_num, int32_t first_user,

@@ -149,6 +149,7 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
     unsigned long long n_replayed = 0;
     float lr_t = 0.f;
     if (FUSE) lr_t = fdiv(fmul(a.lr, fsqrt(fsub(1.0f, a.pw[1]))), fsub(1.0f, a.pw[0]));
+    const bool lr_ok = FUSE && lr_in_replay_range(a.lr);
 
     for (int64_t base = warp_global * GPW; base < a.B; base += n_warps * GPW) {
         const int64_t i = base + gw;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
                 if (gl == 0) n_replayed += (unsigned long long)(a.step_no - done);
 #pragma unroll
                 for (int c = 0; c < C; ++c)
-                    if (gl + G * c < q) lazy_replay4(u[c], mu[c], vu[c], a.lr_hist, done, a.step_no);
+                    if (gl + G * c < q) lazy_replay4_blocked(u[c], mu[c], vu[c], a.lr_hist, done, a.step_no, lr_ok);
             }
         }
         float sp = 0.0f, sn = 0.0f, sq = 0.0f;
@@ -314,6 +315,7 @@ static void launch_step_gc(const StepArgs& a, int grid, cudaStream_t st) {
 
 int launch_bpr_step(const StepArgs& a, cudaStream_t st) {
     if (a.d % 4 != 0 || a.d < 4 || a.d > 512) return 1;
+    if (launch_bpr_step_pipe(a, st) == 0) return 0;      // d = 128, distinct users: the bulk-copy pipeline (pda_step_pipe.cu)
     const int q = a.d / 4;
     int G = 1;
     while (G < q && G < 32) G *= 2;
@@ -374,7 +376,7 @@ __global__ void __launch_bounds__(256) adam_dense_kernel(AdamArgs a) {
         adam_elem(w.z, m.z, v.z, g.z, lr_t);
         adam_elem(w.w, m.w, v.w, g.w, lr_t);
         *W = w; *M = m; *V = v;
-        *Gp = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!a.keep_g) *Gp = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
 
@@ -386,20 +388,26 @@ void launch_adam_dense(const AdamArgs& a, cudaStream_t st) {
     adam_dense_kernel<<<(int)blocks, 256, 0, st>>>(a);
 }
 
-// loss3 = {loss, mf, reg}; beta powers advance (AdamOptimizer._finish); accumulators reset.
-// are the users of a host batch distinct (rd.sample)?  seen[] is an n_users scratch array of tags; a repeated user
-// finds this call's tag already there.  *dup is set to 1 when any user repeats.
-__global__ void users_distinct_kernel(const int32_t* __restrict__ users, int64_t B, int32_t* __restrict__ seen, int32_t tag,
-                                      int32_t* dup) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x)
-        if (atomicExch(seen + users[i], tag) == tag) *dup = 1;
+// Host batches are validated on the device in one pass over the ids: flags[1] is set when any id lies outside its
+// table (the reference's embedding_lookup raises for those -- MF/model_api.py:51-53), and, when `seen` is given (an
+// n_users scratch array of tags), flags[0] is set when a user repeats: a repeated user finds this call's tag already
+// there.  The reference's batches hold distinct users (rd.sample, train_new_api.py:384-385), a host caller may pass anything.
+__global__ void batch_check_kernel(const int32_t* __restrict__ users, const int32_t* __restrict__ pos, const int32_t* __restrict__ neg,
+                                   int64_t B, int32_t n_users, int32_t n_items, int32_t* __restrict__ seen, int32_t tag,
+                                   int32_t* flags) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < B; i += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t u = users[i], p = pos[i], n = neg[i];
+        if ((uint32_t)u >= (uint32_t)n_users || (uint32_t)p >= (uint32_t)n_items || (uint32_t)n >= (uint32_t)n_items) { flags[1] = 1; continue; }
+        if (seen && atomicExch(seen + u, tag) == tag) flags[0] = 1;
+    }
 }
 
-void launch_users_distinct(const int32_t* users, int64_t B, int32_t* seen, int32_t tag, int32_t* dup, cudaStream_t st) {
+void launch_batch_check(const int32_t* users, const int32_t* pos, const int32_t* neg, int64_t B, int32_t n_users,
+                        int32_t n_items, int32_t* seen, int32_t tag, int32_t* flags, cudaStream_t st) {
     int64_t blocks = (B + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
     if (blocks < 1) blocks = 1;
-    users_distinct_kernel<<<(int)blocks, 256, 0, st>>>(users, B, seen, tag, dup);
+    batch_check_kernel<<<(int)blocks, 256, 0, st>>>(users, pos, neg, B, n_users, n_items, seen, tag, flags);
 }
 
 __global__ void fill_i32_kernel(int32_t* p, int64_t n, int32_t value) {
@@ -462,6 +470,7 @@ __global__ void finish_step_kernel(double* loss_acc, float* loss3, double* loss_
     }
 }
 
+// loss3 = {loss, mf, reg}; beta powers advance (AdamOptimizer._finish); accumulators reset.
 void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float* pw, int64_t B, float regs,
                         int batch_size, int advance_powers, float lr, float* lr_slot, cudaStream_t st) {
     finish_step_kernel<<<1, 32, 0, st>>>(loss_acc, loss3, loss_sum, pw, (double)B, (double)regs, (double)batch_size,

@@ -277,6 +277,31 @@ class PDAModel:
         check(self.lib.pda_adam_dense_rows(self._h, self._TABLES[name], int(row_lo), int(row_hi),
                                            ptr(stream) if stream else None))
 
+    def adam_dense_rows_ext(self, name, row_lo, row_hi, grad_ptr, stream=0):
+        """the same sweep with the rows' gradient read from a caller-owned device buffer [row_hi - row_lo, d]
+        (out-of-place reduce-scatter output); the model's own accumulator is not touched."""
+        check(self.lib.pda_adam_dense_rows_ext(self._h, self._TABLES[name], int(row_lo), int(row_hi), ptr(int(grad_ptr)),
+                                               ptr(stream) if stream else None))
+
+    def stage_batch_async(self, users, pos_items, neg_items, pos_pop=None, neg_pop=None, copy_stream=0):
+        """enqueue the host->device copies (+ the id / distinct-users check) of a PINNED host batch on `copy_stream` and
+        return; staged_batch_wait() completes it.  The arrays must stay alive until then."""
+        u, p, n = _i32(users), _i32(pos_items), _i32(neg_items)
+        pp = None if pos_pop is None else _f32(pos_pop)
+        npop = None if neg_pop is None else _f32(neg_pop)
+        self._staged_keepalive = (u, p, n, pp, npop)
+        check(self.lib.pda_stage_batch_host_async(self._h, ptr(u), ptr(p), ptr(n), ptr(pp), ptr(npop), len(u),
+                                                  ptr(copy_stream) if copy_stream else None))
+        return len(u)
+
+    def staged_batch_wait(self, stream=0):
+        check(self.lib.pda_staged_batch_wait(self._h, ptr(stream) if stream else None))
+        self._staged_keepalive = None
+
+    def read_loss_async(self, pinned_dst, stream=0):
+        """loss3 of the last enqueued step -> a pinned fp32[3] view (pinned_array), no synchronisation"""
+        check(self.lib.pda_read_loss_async(self._h, ptr(pinned_dst), ptr(stream) if stream else None))
+
     def stage_batch(self, users, pos_items, neg_items, pos_pop=None, neg_pop=None, stream=0):
         u, p, n = _i32(users), _i32(pos_items), _i32(neg_items)
         pp = None if pos_pop is None else _f32(pos_pop)

@@ -3,14 +3,23 @@
 Partition: USERS are split into contiguous shards, one per rank; every rank samples its B triples from
 its own users (rank-local sampling), so user rows, user gradients and the user table's Adam state never
 leave the GPU.  The ITEM table (small: n_items x d) is replicated; its gradient is the one real exchange
-step.  Default ("scatter", when n_items divides by the world size): NCCL reduce-scatter of the dense
-item-gradient accumulator -> every rank runs the Adam sweep on ITS row slice only (1/world of the sweep, and
-only that slice of the item Adam slots is live) -> NCCL all-gather of the updated rows, waited for right
-before the next step's kernel reads the table.  Fallback ("allreduce"): all-reduce of the gradient in row
-chunks pipelined with the full dense sweep on every rank.  Either way the result equals a single-process
-step on the union batch of world*B triples (loss mean and L2 divisor use the global batch).
+step.  Default ("scatter", when n_items divides by the world size), per step:
 
-torch.distributed is plumbing: it owns the NCCL communicator and the stream; the kernels are the library's.
+    sampler k+1 (side stream)  ||  step kernel k -> reduce-scatter (out of place) -> sliced Adam -> all-gather
+                                                      \\-> zero the accumulator (side stream, under the all-gather)
+
+  * NCCL reduce-scatter of the dense item-gradient accumulator into a separate [rows/world, d] buffer, so the
+    accumulator is free to be zeroed while the all-gather runs;
+  * every rank runs the Adam sweep on ITS row slice only (1/world of the sweep; only that slice of the item
+    Adam slots is live -- sync_item_slots() all-gathers them for checkpoints);
+  * NCCL all-gather of the updated rows, waited for right before the next step kernel reads the table;
+  * the sampler of step k+1 (or the host->device copies of host batch k+1) starts when step k's kernel has read
+    the batch buffers and runs under the exchange.
+Fallback ("allreduce"): all-reduce of the gradient in row chunks pipelined with the full dense sweep on every
+rank.  Either way the result equals a single-process step on the union batch of world*B triples (loss mean and
+L2 divisor use the global batch).
+
+torch.distributed is plumbing: it owns the NCCL communicator and the streams; the kernels are the library's.
 With world == 1 this class adds nothing to the single-GPU path.
 """
 from __future__ import annotations
@@ -31,6 +40,14 @@ def shard_range(n, world, rank):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 class ShardedTrainer:
     def __init__(self, model, world=1, rank=0, reducer=None, chunks=4, exchange=None):
         """reducer(tensor) -> None sums `tensor` in place over ranks (default: torch.distributed.all_reduce).
@@ -40,7 +57,12 @@ class ShardedTrainer:
         self._wi = None
         self._pending = None
         self._own = None
+        self._gslice = None
+        self._cuda = hasattr(model, "lib")      # the GPU model (host stand-ins of the tests run the same logic on CPU)
+        self._side = self._zs = self._copy = None
+        self._zero_pending = False
         exchange = exchange or os.environ.get("PDA_DP_EXCHANGE", "scatter")
+        self.exchange = exchange
         if int(world) > 1 and getattr(model, "train", "") == "temp_pop":
             raise NotImplementedError("data-parallel training covers BPRMF / PD / PDG (the bias tables of BPR(t)-pop are not exchanged)")
         self._gi = self._acc = None
@@ -56,28 +78,48 @@ class ShardedTrainer:
             import torch.distributed as dist
             if reducer is None:
                 self._reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
-                if hasattr(model, "lib"):     # the GPU model: split optimizer + asynchronous NCCL work handles
+                if hasattr(model, "adam_dense_rows_ext"):     # split optimizer available: asynchronous work handles
                     self._async_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
+            scatter_ok = exchange == "scatter" and self._async_reduce is not None and model.n_items % self.world == 0
             if hasattr(model, "exchange_tensors"):     # host stand-ins (tests) hand their buffers over directly
-                self._gi, self._acc = model.exchange_tensors()
+                ex = model.exchange_tensors()
+                self._gi, self._acc = ex[0], ex[1]
+                if scatter_ok and len(ex) > 2:
+                    self._wi = ex[2]
             else:
                 dev = torch.device("cuda", model.device)
                 self._gi = torch.as_tensor(_DevArray(model.grad_ptr("item_embedding"), (model.n_items, model.emb_dim),
                                                      "<f4"), device=dev)
                 self._acc = torch.as_tensor(_DevArray(model.loss_acc_ptr(), (2,), "<f8"), device=dev)
-                if exchange == "scatter" and self._async_reduce is not None and model.n_items % self.world == 0:
+                if scatter_ok:
                     self._wi = torch.as_tensor(_DevArray(model.table_ptr("item_embedding"), (model.n_items, model.emb_dim),
                                                          "<f4"), device=dev)
-                    rows = model.n_items // self.world
-                    self._own = (self.rank * rows, (self.rank + 1) * rows)
+                self._side, self._zs, self._copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+            if self._wi is not None:
+                rows = model.n_items // self.world
+                self._own = (self.rank * rows, (self.rank + 1) * rows)
+                self._gslice = torch.empty((rows, model.emb_dim), dtype=torch.float32, device=self._gi.device)
+
+    # ---- stream plumbing: the library enqueues on the raw `stream`; torch (NCCL, memsets) must order against the same one
+    def _cs(self, stream):
+        if not self._cuda:
+            return None
+        import torch
+        return torch.cuda.ExternalStream(stream) if stream else torch.cuda.default_stream(self._gi.device)
+
+    def _on(self, cs):
+        if cs is None:
+            return _NullCtx()
+        import torch
+        return torch.cuda.stream(cs)
 
     def _exchange(self):
         self._reduce(self._gi)     # dense item-gradient block, summed over ranks (NVLink / NVSwitch)
         self._reduce(self._acc)    # 2 doubles: loss partial sums -> global mean
 
-    def _exchange_and_apply(self, stream):
-        """item-gradient all-reduce overlapped with the rank-local half of the optimizer: the user table's gradient
-        never leaves the GPU, so its Adam update runs on the compute stream while NCCL moves the item gradient."""
+    def _exchange_and_apply(self, stream, cs=None):
+        """item-gradient exchange + optimizer.  The user table's gradient never leaves the GPU: its Adam update runs on
+        the compute stream (or already ran inside the step kernel) while NCCL moves the item gradient."""
         m = self.model
         if self._async_reduce is None:
             self._exchange()
@@ -86,16 +128,20 @@ class ShardedTrainer:
         if self._own is not None:
             import torch.distributed as dist
             lo, hi = self._own
-            # in place: this rank's slice of the accumulator receives the sum over ranks of that slice
-            w_rs = dist.reduce_scatter_tensor(self._gi[lo:hi], self._gi, op=dist.ReduceOp.SUM, async_op=True)
+            # out of place: the sum over ranks of this rank's row slice lands in _gslice; the accumulator is only read
+            w_rs = dist.reduce_scatter_tensor(self._gslice, self._gi, op=dist.ReduceOp.SUM, async_op=True)
             wacc = self._async_reduce(self._acc)
             m.adam_apply(stream, part=1)          # rank-local tables (nothing when the step kernel already did it)
             w_rs.wait()                           # stream-level dependency, the host does not block
-            m.adam_dense_rows("item_embedding", lo, hi, stream)      # consumes and zeroes rows [lo, hi) of the accumulator
-            if lo > 0:
-                self._gi[:lo].zero_()             # the other slices hold this rank's partial sums
-            if hi < m.n_items:
-                self._gi[hi:].zero_()
+            if cs is not None:                    # the accumulator has been consumed: zero it under the all-gather
+                self._zs.wait_stream(cs)
+                with self._on(self._zs):
+                    self._gi.zero_()
+                self._zero_pending = True
+            else:
+                self._gi.zero_()
+            g = self._gslice if not self._cuda else self._gslice.data_ptr()
+            m.adam_dense_rows_ext("item_embedding", lo, hi, g, stream)
             self._pending = dist.all_gather_into_tensor(self._wi, self._wi[lo:hi], async_op=True)
             wacc.wait()
             m.adam_apply(stream, part=8)
@@ -120,30 +166,108 @@ class ShardedTrainer:
             m.train_sampled(seed, epoch, step0, n_steps, B, stream)
             return
         m.set_global_batch(B * self.world)
-        for k in range(n_steps):
-            m.sample_batch(seed, epoch, step0 + k, B, stream, fetch=False)      # overlaps the all-gather of the last step
-            self.finish()
-            m.forward_backward_device(B, stream)
-            self._exchange_and_apply(stream)
-        self.finish()
+        cs = self._cs(stream)
+        with self._on(cs):
+            if cs is None or self._side is None:
+                for k in range(n_steps):
+                    m.sample_batch(seed, epoch, step0 + k, B, stream, fetch=False)
+                    self.finish(cs)
+                    m.forward_backward_device(B, stream)
+                    self._exchange_and_apply(stream, cs)
+                self.finish(cs)
+                return
+            side = self._side
+            side.wait_stream(cs)            # earlier work on the compute stream may still read the batch buffers
+            m.sample_batch(seed, epoch, step0, B, side.cuda_stream, fetch=False)
+            for k in range(n_steps):
+                cs.wait_stream(side)        # batch k is sampled
+                self.finish(cs)             # item table complete (all-gather of step k-1), accumulator zeroed
+                m.forward_backward_device(B, stream)
+                if k + 1 < n_steps:         # the sampler of step k+1 runs under step k's exchange
+                    side.wait_stream(cs)
+                    m.sample_batch(seed, epoch, step0 + k + 1, B, side.cuda_stream, fetch=False)
+                self._exchange_and_apply(stream, cs)
+            self.finish(cs)
 
-    def finish(self):
-        """the item table is complete on this rank's compute stream (all-gather of the last step done)"""
+    def finish(self, cs=None):
+        """the item table is complete on this rank's compute stream (all-gather of the last step done) and the
+        gradient accumulator is zero again"""
         if self._pending is not None:
             self._pending.wait()
             self._pending = None
+        if self._zero_pending:
+            import torch
+            (cs if cs is not None else torch.cuda.current_stream()).wait_stream(self._zs)
+            self._zero_pending = False
 
     def train_step_host(self, users, pos, neg, pos_pop=None, neg_pop=None, stream=0):
         m = self.model
         if self.world == 1:
             return m.train_step(users, pos, neg, pos_pop, neg_pop)
         m.set_global_batch(len(users) * self.world)
-        B = m.stage_batch(users, pos, neg, pos_pop, neg_pop, stream)
-        self.finish()
-        m.forward_backward_device(B, stream)
-        self._exchange_and_apply(stream)
-        self.finish()
+        cs = self._cs(stream)
+        with self._on(cs):
+            B = m.stage_batch(users, pos, neg, pos_pop, neg_pop, stream)
+            self.finish(cs)
+            m.forward_backward_device(B, stream)
+            self._exchange_and_apply(stream, cs)
+            self.finish(cs)
         return m.read_loss(stream)
+
+    def train_steps_host(self, users, pos, neg, pos_pop=None, neg_pop=None, stream=0):
+        """n consecutive steps from PINNED host arrays [n, B] (PDAModel.pinned_array): the host->device copies of
+        batch k+1 (and the device-side id / distinct-users check) run on a copy stream under step k's gradient
+        exchange; one async D2H of the 3 loss scalars per step.  Returns the [n, 3] losses; same results as n calls
+        of train_step_host."""
+        import numpy as np
+        m = self.model
+        n, B = users.shape
+        if self.world == 1:
+            return m.train_steps(users, pos, neg, pos_pop, neg_pop)
+        m.set_global_batch(B * self.world)
+        cs = self._cs(stream)
+        ring = m.pinned_array((n, 4), np.float32)
+        pp = (lambda k: None) if pos_pop is None else (lambda k: pos_pop[k])
+        pn = (lambda k: None) if neg_pop is None else (lambda k: neg_pop[k])
+        with self._on(cs):
+            self._copy.wait_stream(cs)
+            m.stage_batch_async(users[0], pos[0], neg[0], pp(0), pn(0), self._copy.cuda_stream)
+            for k in range(n):
+                m.staged_batch_wait(stream)          # the HOST waits for batch k's copies only
+                self.finish(cs)
+                m.forward_backward_device(B, stream)
+                if k + 1 < n:
+                    self._copy.wait_stream(cs)       # the step kernel has read the batch buffers
+                    m.stage_batch_async(users[k + 1], pos[k + 1], neg[k + 1], pp(k + 1), pn(k + 1), self._copy.cuda_stream)
+                self._exchange_and_apply(stream, cs)
+                m.read_loss_async(ring[k], stream)
+            self.finish(cs)
+        m.synchronize()
+        return np.array(ring[:, :3])
+
+    def sync_item_slots(self):
+        """scatter mode keeps only this rank's row slice of the item Adam slots (m, v) live; all-gather them so that
+        every rank holds the full state (checkpoints, switching to the all-reduce exchange or to one GPU)."""
+        if self._own is None:
+            return
+        import torch
+        import torch.distributed as dist
+        self.finish()
+        lo, hi = self._own
+        m = self.model
+        for name in ("item_m", "item_v"):
+            if self._cuda:
+                t = torch.as_tensor(_DevArray(m.table_ptr(name), (m.n_items, m.emb_dim), "<f4"), device=self._gi.device)
+            else:
+                t = m.slot_tensor(name)
+            dist.all_gather_into_tensor(t, t[lo:hi].clone())
+        if self._cuda:
+            torch.cuda.synchronize()
+
+    def state_dict(self):
+        """PDAModel.state_dict() of this rank with complete item Adam slots (rank-local user rows)."""
+        self.sync_item_slots()
+        return self.model.state_dict()
 
 
 class ShardedEvaluator:

@@ -37,7 +37,12 @@ class HostStandIn:
         self.Bg = 0
 
     def exchange_tensors(self):
-        return self.GI, self.acc
+        import torch
+        return self.GI, self.acc, torch.from_numpy(self.I)       # the item table shares memory with self.I
+
+    def slot_tensor(self, name):
+        import torch
+        return torch.from_numpy(self.aI.m if name == "item_m" else self.aI.v)
 
     def set_global_batch(self, Bg):
         self.Bg = Bg
@@ -63,24 +68,43 @@ class HostStandIn:
         self.acc[0] += -float(r["mf_loss"]) * len(users)
         self.acc[1] += float(r["reg_loss"]) * self.batch_size / (0.5 * float(np.float32(self.regs)))
 
-    def adam_apply(self, stream=0):
+    # the split optimizer of PDAModel: part 1 = rank-local (user) table, part 2 = dense item sweep + bookkeeping,
+    # part 8 = bookkeeping only (the item sweep ran in row ranges)
+    def adam_apply(self, stream=0, part=3):
         po = self.po
         lr_t = self.pw.lr_t(self.lr)
-        po.adam_apply_dense(self.U, self.aU, self.GU, lr_t)
-        po.adam_apply_dense(self.I, self.aI, self.GI.numpy().copy(), lr_t)
-        self.pw.finish()
-        mf = -float(self.acc[0]) / self.Bg
-        reg = float(np.float32(self.regs)) * 0.5 * float(self.acc[1]) / self.batch_size
-        self.loss3 = (mf + reg, mf, reg)
-        self.GU[:] = 0
-        self.GI.zero_()
-        self.acc.zero_()
+        if part & 1:
+            po.adam_apply_dense(self.U, self.aU, self.GU, lr_t)
+            self.GU[:] = 0
+        if part & 2:
+            self.adam_dense_rows("item_embedding", 0, self.n_items)
+        if part & (2 | 8):
+            self.pw.finish()
+            mf = -float(self.acc[0]) / self.Bg
+            reg = float(np.float32(self.regs)) * 0.5 * float(self.acc[1]) / self.batch_size
+            self.loss3 = (mf + reg, mf, reg)
+            self.acc.zero_()
+
+    def _item_rows(self, lo, hi, G):
+        po = self.po
+        st = po.AdamState((hi - lo, self.emb_dim))
+        st.m, st.v = self.aI.m[lo:hi], self.aI.v[lo:hi]
+        W = self.I[lo:hi]
+        po.adam_apply_dense(W, st, G, self.pw.lr_t(self.lr))      # W is a view: updated in place
+        self.aI.m[lo:hi], self.aI.v[lo:hi] = st.m, st.v
+
+    def adam_dense_rows(self, name, lo, hi, stream=0):
+        self._item_rows(lo, hi, self.GI.numpy()[lo:hi].copy())
+        self.GI[lo:hi] = 0
+
+    def adam_dense_rows_ext(self, name, lo, hi, grad, stream=0):
+        self._item_rows(lo, hi, grad.numpy().copy())
 
     def read_loss(self, stream=0):
         return self.loss3
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, exchange="scatter"):
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
     from pda_b200.parallel import ShardedTrainer, shard_range
@@ -93,7 +117,8 @@ def _worker(rank, world, port, q):
         I = rng.normal(0, 0.3, (n_items, d)).astype(np.float32)
         lo, hi = shard_range(n_users, world, rank)
         model = HostStandIn(U[lo:hi], I, 1e-2, 1e-3, B * world)
-        tr = ShardedTrainer(model, world, rank)
+        tr = ShardedTrainer(model, world, rank, exchange=exchange)
+        assert (tr._own is not None) == (exchange == "scatter")
         losses = []
         for step in range(4):
             srng = np.random.default_rng(100 + step)
@@ -105,13 +130,15 @@ def _worker(rank, world, port, q):
                                 srng.integers(0, n_items, B).astype(np.int32), srng.random(B).astype(np.float32),
                                 srng.random(B).astype(np.float32)))
             losses.append(tr.train_step_host(*batches[rank]))
-        q.put((rank, lo, hi, model.U, model.I, losses))
+        tr.sync_item_slots()                                   # scatter: every rank ends with the full item Adam slots
+        q.put((rank, lo, hi, model.U, model.I, losses, model.aI.m.copy(), model.aI.v.copy()))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_two_ranks_equal_one_process_on_the_union_batch():
+@pytest.mark.parametrize("exchange", ["scatter", "allreduce"])
+def test_two_ranks_equal_one_process_on_the_union_batch(exchange):
     import torch.multiprocessing as mp
     from oracle import pda_oracle as po
     from pda_b200.parallel import shard_range
@@ -119,7 +146,7 @@ def test_two_ranks_equal_one_process_on_the_union_batch():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     world = 2
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, exchange)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=240) for _ in range(world)], key=lambda x: x[0])
@@ -146,10 +173,13 @@ def test_two_ranks_equal_one_process_on_the_union_batch():
     I0, I1 = res[0][4], res[1][4]
     assert np.array_equal(I0, I1)                                   # replicas stay identical
     assert np.abs(I0 - om.I).max() <= 2e-5 * np.abs(om.I).max()     # = the union-batch step (fp32 sum order differs)
-    for rank, lo, hi, Ur, _, losses in res:
+    for rank, lo, hi, Ur, _, losses, mI, vI in res:
         assert np.abs(Ur - om.U[lo:hi]).max() <= 2e-5 * np.abs(om.U).max()
         for got, want in zip(losses, ref_losses):
             assert np.allclose(got, want, rtol=1e-5)
+        # item Adam slots complete on every rank (scatter: after sync_item_slots)
+        assert np.abs(mI - om.aI.m).max() <= 2e-5 * np.abs(om.aI.m).max()
+        assert np.abs(vI - om.aI.v).max() <= 2e-5 * np.abs(om.aI.v).max()
 
 
 # ---------------------------------------------------------------------------------------------
