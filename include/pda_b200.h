@@ -254,6 +254,14 @@ int pda_metrics_host(pda_model* m, const int32_t* ids, int64_t M, int Kkeep, con
                      const int64_t* truth_indptr, const int32_t* truth_items, int64_t n_truth_rows, const int32_t* Ks,
                      int nK, double* out);
 
+/* diagnostics behind the bit-exactness claims of the exact Adam replay: runs a check kernel on the current device and
+ * returns out5 = {operands checked, mismatching results, first mismatch: 3 raw words}.
+ *   kind 3: every fp32 bit pattern in [lo_or_seed, hi] through the straight-line sqrt refinement vs __fsqrt_rn
+ *   kind 0: per_thread x 2 x 303104 random in-range (a, b) pairs through the straight-line quotient vs __fdiv_rn
+ *   kind 1 / 2: per_thread x 4 x 303104 random in-range elements through one packed zero-gradient / gradient Adam step
+ *               vs the generic separately rounded form (pda_common.cuh) */
+int pda_debug_numerics(int kind, uint32_t lo_or_seed, uint32_t hi, uint64_t per_thread, uint64_t* out5);
+
 #ifdef __cplusplus
 }
 #endif
