@@ -115,3 +115,20 @@ def test_product_package_never_imports_the_oracle():
                     txt = open(os.path.join(dirpath, f), errors="ignore").read()
                     assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), os.path.join(dirpath, f)
                     assert not re.search(r"#include[^\n]*oracle|libpda_oracle|libref_eval", txt), os.path.join(dirpath, f)
+
+
+def test_no_contracted_adam_decay_in_sass():
+    """ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (one rounding instead of two): the Adam moment updates
+    m*b1 + g*(1-b1), v*b2 + g*g*(1-b2) must stay separately rounded in EVERY kernel -- no FFMA / FFMA2 may carry the decay
+    constants as an immediate (the exact replay is bit-compared against the dense sweep)."""
+    import re
+    import shutil
+    import subprocess
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe):
+        pytest.skip("cuobjdump not available")
+    from pda_b200 import _lib
+    sass = subprocess.run([exe, "-sass", _lib.SO_PATH], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass and "UTCHMMA" in sass            # the bulk-copy step pipeline and the tcgen05 sweep are in the build
+    bad = [l for l in sass.splitlines() if re.search(r"FFMA2?\b.*(0\.8999999|0\.9990000|0\.1000000238|0\.00099998)", l)]
+    assert not bad, bad[:5]
