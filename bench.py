@@ -221,6 +221,8 @@ def run_ours(a):
     if a.adam != "dense":
         model.adam_stats(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        trainer.profile(True)       # per-phase events of the gradient exchange (rank-local, on the compute stream)
     barrier()
     tw0 = time.time()
     e0.record()
@@ -230,6 +232,9 @@ def run_ours(a):
     tw1 = time.time()
     step_no += a.steps
     ms = e0.elapsed_time(e1)
+    exch = trainer.profile_summary() if world > 1 else None
+    if world > 1:
+        trainer.profile(False)
     prof = model.profile_read()
     model.profile(False)
     rows_updated, row_steps_replayed = model.adam_stats(reset=True) if a.adam != "dense" else (0, 0)
@@ -354,7 +359,7 @@ def run_ours(a):
                "warmup": a.warmup, "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                "config": dict(make_config(a, world), adam_evaluation=a.adam),
-               "roofline": roof, "kernels": kern, "cpu_baseline": cpu, "e2e": e2e, "eval": ev, "parity": parity,
+               "roofline": roof, "kernels": kern, "exchange": exch, "cpu_baseline": cpu, "e2e": e2e, "eval": ev, "parity": parity,
                "gpu_launches": int(step_n + adam_n + cat_n + samp_n + a.steps), "clocks": clk,
                "last_loss": [float(x) for x in loss]}
         json_out.write(json.dumps(out) + "\n")

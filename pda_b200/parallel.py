@@ -55,12 +55,13 @@ class ShardedTrainer:
         import os
         self.model, self.world, self.rank = model, int(world), int(rank)
         self._wi = None
-        self._pending = None
         self._own = None
         self._gslice = None
         self._cuda = hasattr(model, "lib")      # the GPU model (host stand-ins of the tests run the same logic on CPU)
         self._side = self._zs = self._copy = None
         self._zero_pending = False
+        self._pending = []
+        self.nch = 1
         exchange = exchange or os.environ.get("PDA_DP_EXCHANGE", "scatter")
         self.exchange = exchange
         if int(world) > 1 and getattr(model, "train", "") == "temp_pop":
@@ -96,9 +97,27 @@ class ShardedTrainer:
                                                          "<f4"), device=dev)
                 self._side, self._zs, self._copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
             if self._wi is not None:
-                rows = model.n_items // self.world
-                self._own = (self.rank * rows, (self.rank + 1) * rows)
-                self._gslice = torch.empty((rows, model.emb_dim), dtype=torch.float32, device=self._gi.device)
+                # The exchange runs in `nch` row chunks; inside chunk c (rows [c R, (c+1) R), R = n_items / nch) rank r
+                # owns rows [c R + r R/world, c R + (r+1) R/world).  Reduce-scatter of chunk c+1 (send-heavy with in-switch
+                # reduction) and all-gather of chunk c (receive-heavy with multicast) travel on two communicators and
+                # overlap; so does the sliced Adam sweep.
+                nch = int(os.environ.get("PDA_DP_CHUNKS", "4"))
+                while nch > 1 and model.n_items % (nch * self.world) != 0:
+                    nch -= 1
+                self.nch = nch
+                R = model.n_items // nch
+                sub = R // self.world
+                self._own = [(c * R + self.rank * sub, c * R + (self.rank + 1) * sub) for c in range(nch)]
+                self._chunk = [(c * R, (c + 1) * R) for c in range(nch)]
+                self._gslice = [torch.empty((sub, model.emb_dim), dtype=torch.float32, device=self._gi.device) for _ in range(nch)]
+                self._pg_ag = None
+                if self._cuda and nch > 1 and os.environ.get("PDA_DP_TWO_COMMS", "1") != "0":
+                    try:
+                        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                        self._pg_ag = dist.new_group(backend="nccl", pg_options=opts)
+                    except Exception:
+                        self._pg_ag = dist.new_group(backend="nccl")
+        self._prof = None
 
     # ---- stream plumbing: the library enqueues on the raw `stream`; torch (NCCL, memsets) must order against the same one
     def _cs(self, stream):
@@ -112,6 +131,35 @@ class ShardedTrainer:
             return _NullCtx()
         import torch
         return torch.cuda.stream(cs)
+
+    # ---- optional per-phase timeline (CUDA events on the compute stream) ----
+    def profile(self, on=True):
+        self._prof = {"fwd": [], "rs": [], "adam": [], "ag": []} if on else None
+
+    def _mark(self, name):
+        if self._prof is None or not self._cuda:
+            return
+        import torch
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self._prof[name].append(e)
+
+    def profile_summary(self):
+        """mean ms per step on the compute stream: step kernel end -> last reduce-scatter chunk waited (`rs`: exposed
+        reduce-scatter), -> last sliced Adam sweep enqueued and done (`adam`), -> all-gather waited by the next step
+        (`ag`: exposed all-gather, the sampler of the next step runs under it)."""
+        if self._prof is None or not self._prof["fwd"]:
+            return None
+        import torch
+        torch.cuda.synchronize()
+        p = self._prof
+        n = min(len(p["fwd"]), len(p["rs"]), len(p["adam"]), len(p["ag"]))
+        out = {"steps": n, "chunks": self.nch, "two_communicators": self._pg_ag is not None}
+        out["rs_exposed_ms"] = sum(p["fwd"][i].elapsed_time(p["rs"][i]) for i in range(n)) / n
+        out["adam_after_rs_ms"] = sum(p["rs"][i].elapsed_time(p["adam"][i]) for i in range(n)) / n
+        out["ag_exposed_ms"] = sum(p["adam"][i].elapsed_time(p["ag"][i]) for i in range(n)) / n
+        out["exchange_total_ms"] = sum(p["fwd"][i].elapsed_time(p["ag"][i]) for i in range(n)) / n
+        return out
 
     def _exchange(self):
         self._reduce(self._gi)     # dense item-gradient block, summed over ranks (NVLink / NVSwitch)
@@ -127,22 +175,27 @@ class ShardedTrainer:
             return
         if self._own is not None:
             import torch.distributed as dist
-            lo, hi = self._own
-            # out of place: the sum over ranks of this rank's row slice lands in _gslice; the accumulator is only read
-            w_rs = dist.reduce_scatter_tensor(self._gslice, self._gi, op=dist.ReduceOp.SUM, async_op=True)
+            # out of place: the sum over ranks of this rank's rows of chunk c lands in _gslice[c]; the accumulator is only read
+            w_rs = [dist.reduce_scatter_tensor(self._gslice[c], self._gi[lo:hi], op=dist.ReduceOp.SUM, async_op=True)
+                    for c, (lo, hi) in enumerate(self._chunk)]
             wacc = self._async_reduce(self._acc)
             m.adam_apply(stream, part=1)          # rank-local tables (nothing when the step kernel already did it)
-            w_rs.wait()                           # stream-level dependency, the host does not block
-            if cs is not None:                    # the accumulator has been consumed: zero it under the all-gather
-                self._zs.wait_stream(cs)
-                with self._on(self._zs):
-                    self._gi.zero_()
-                self._zero_pending = True
-            else:
-                self._gi.zero_()
-            g = self._gslice if not self._cuda else self._gslice.data_ptr()
-            m.adam_dense_rows_ext("item_embedding", lo, hi, g, stream)
-            self._pending = dist.all_gather_into_tensor(self._wi, self._wi[lo:hi], async_op=True)
+            for c, (lo, hi) in enumerate(self._own):
+                w_rs[c].wait()                    # stream-level dependency, the host does not block
+                if c == self.nch - 1:             # the accumulator has been consumed: zero it under the all-gather
+                    self._mark("rs")
+                    if cs is not None:
+                        self._zs.wait_stream(cs)
+                        with self._on(self._zs):
+                            self._gi.zero_()
+                        self._zero_pending = True
+                    else:
+                        self._gi.zero_()
+                g = self._gslice[c] if not self._cuda else self._gslice[c].data_ptr()
+                m.adam_dense_rows_ext("item_embedding", lo, hi, g, stream)
+                clo, chi = self._chunk[c]
+                self._pending.append(dist.all_gather_into_tensor(self._wi[clo:chi], self._wi[lo:hi], group=self._pg_ag, async_op=True))
+            self._mark("adam")
             wacc.wait()
             m.adam_apply(stream, part=8)
             return
@@ -183,6 +236,7 @@ class ShardedTrainer:
                 cs.wait_stream(side)        # batch k is sampled
                 self.finish(cs)             # item table complete (all-gather of step k-1), accumulator zeroed
                 m.forward_backward_device(B, stream)
+                self._mark("fwd")
                 if k + 1 < n_steps:         # the sampler of step k+1 runs under step k's exchange
                     side.wait_stream(cs)
                     m.sample_batch(seed, epoch, step0 + k + 1, B, side.cuda_stream, fetch=False)
@@ -192,9 +246,11 @@ class ShardedTrainer:
     def finish(self, cs=None):
         """the item table is complete on this rank's compute stream (all-gather of the last step done) and the
         gradient accumulator is zero again"""
-        if self._pending is not None:
-            self._pending.wait()
-            self._pending = None
+        if self._pending:
+            for w in self._pending:
+                w.wait()
+            self._pending = []
+            self._mark("ag")
         if self._zero_pending:
             import torch
             (cs if cs is not None else torch.cuda.current_stream()).wait_stream(self._zs)
@@ -253,14 +309,14 @@ class ShardedTrainer:
         import torch
         import torch.distributed as dist
         self.finish()
-        lo, hi = self._own
         m = self.model
         for name in ("item_m", "item_v"):
             if self._cuda:
                 t = torch.as_tensor(_DevArray(m.table_ptr(name), (m.n_items, m.emb_dim), "<f4"), device=self._gi.device)
             else:
                 t = m.slot_tensor(name)
-            dist.all_gather_into_tensor(t, t[lo:hi].clone())
+            for (lo, hi), (clo, chi) in zip(self._own, self._chunk):
+                dist.all_gather_into_tensor(t[clo:chi], t[lo:hi].clone())
         if self._cuda:
             torch.cuda.synchronize()
 

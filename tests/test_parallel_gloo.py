@@ -112,13 +112,14 @@ def _worker(rank, world, port, q, exchange="scatter"):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         rng = np.random.default_rng(0)                         # same data on every rank
-        n_users, n_items, d, B = 120, 50, 16, 32
+        n_users, n_items, d, B = 120, 48, 16, 32
         U = rng.normal(0, 0.3, (n_users, d)).astype(np.float32)
         I = rng.normal(0, 0.3, (n_items, d)).astype(np.float32)
         lo, hi = shard_range(n_users, world, rank)
         model = HostStandIn(U[lo:hi], I, 1e-2, 1e-3, B * world)
         tr = ShardedTrainer(model, world, rank, exchange=exchange)
         assert (tr._own is not None) == (exchange == "scatter")
+        assert exchange != "scatter" or tr.nch == 4      # 48 item rows: 4 exchange chunks of 12 rows, 6 per rank
         losses = []
         for step in range(4):
             srng = np.random.default_rng(100 + step)
@@ -155,7 +156,7 @@ def test_two_ranks_equal_one_process_on_the_union_batch(exchange):
         assert p.exitcode == 0
     # single process, union batch (global user ids), same init
     rng = np.random.default_rng(0)
-    n_users, n_items, d, B = 120, 50, 16, 32
+    n_users, n_items, d, B = 120, 48, 16, 32
     U = rng.normal(0, 0.3, (n_users, d)).astype(np.float32)
     I = rng.normal(0, 0.3, (n_items, d)).astype(np.float32)
     om = po.OracleModel(n_users, n_items, d, 1e-2, 1e-3, B * world, "s_condition", U=U, I=I)
