@@ -192,6 +192,14 @@ int pda_adam_dense_rows(pda_model* m, int which, int64_t row_lo, int64_t row_hi,
 /* the same sweep with the gradient of those rows taken from a caller-owned DEVICE buffer grad[row_hi - row_lo, d] (the
  * output of an out-of-place reduce-scatter); the buffer is left as it is, the model's own accumulator is not touched */
 int pda_adam_dense_rows_ext(pda_model* m, int which, int64_t row_lo, int64_t row_hi, const float* grad, void* stream);
+/* Data-parallel exchange over NVLink multicast.  pda_adopt_item_buffers moves the item table and its gradient accumulator
+ * into caller-owned device memory ([n_items, d] fp32 each; symmetric memory bound to a multicast object), keeping the
+ * contents; the buffers must outlive the model.  pda_dp_exchange_adam is reduce-scatter + TF1 Adam sweep of rows
+ * [row_lo, row_hi) + all-gather in ONE kernel: mcG / mcW are the MULTICAST addresses of the adopted accumulator / table
+ * (multimem.ld_reduce sums the accumulators of all ranks in the switch, multimem.st writes the updated rows to every
+ * replica).  The caller brackets it with two cross-rank barriers on `stream` and zeroes the accumulator afterwards. */
+int pda_adopt_item_buffers(pda_model* m, float* W_ext, float* G_ext);
+int pda_dp_exchange_adam(pda_model* m, const float* mcG, float* mcW, int64_t row_lo, int64_t row_hi, void* stream);
 int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                          const float* pos_pop, const float* neg_pop, int64_t B, void* stream);
 /* pda_stage_batch_host without blocking: the copies and the device-side id check (ids inside their tables, users

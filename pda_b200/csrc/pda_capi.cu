@@ -49,6 +49,7 @@ struct pda_model {
     int32_t* chk_pinned;               // pinned mirror of chk_flags
     cudaEvent_t ev_staged; int staged_pending;   // pda_stage_batch_host_async / pda_staged_batch_wait
     int32_t max_time;                  // largest stage label of the host-validated train CSR (-1: unknown)
+    int item_ext;                      // W[1] / G[1] live in caller-owned (symmetric) memory: not freed here
     float* pw;          // {beta1_power, beta2_power}
     double* loss_acc;   // {sum log(sigmoid+1e-10), sum of squares}
     float* loss3;       // device {loss, mf, reg}
@@ -206,6 +207,7 @@ void pda_destroy(pda_model* m) {
     if (!m) return;
     cudaSetDevice(m->cfg.device);
     cudaDeviceSynchronize();
+    if (m->item_ext) { m->W[1] = nullptr; m->G[1] = nullptr; }
     for (int t = 0; t < 4; ++t) { cudaFree(m->W[t]); cudaFree(m->Mo[t]); cudaFree(m->Vo[t]); cudaFree(m->G[t]); }
     for (int t = 0; t < 2; ++t) { cudaFree(m->applied[t]); cudaFree(m->stamp[t]); }
     cudaFree(m->lr_hist); cudaFree(m->lazy_stats); cudaFree(m->seen); cudaFree(m->chk_flags);
@@ -704,6 +706,41 @@ int pda_adam_dense_rows_ext(pda_model* m, int which, int64_t row_lo, int64_t row
     a.n4[0] = (row_hi - row_lo) * m->d / 4;
     a.pw = m->pw; a.lr = m->cfg.lr; a.keep_g = 1;
     { ProfScope ps(m, PDA_PROF_ADAM, (cudaStream_t)stream); launch_adam_dense(a, (cudaStream_t)stream); }
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
+// Move the item table and its gradient accumulator into caller-owned device memory (symmetric / multicast-mapped
+// buffers of a data-parallel group): current contents are copied, the library's own arrays are released, and every
+// kernel of the model uses the new storage from now on.  The caller keeps the buffers alive until pda_destroy.
+int pda_adopt_item_buffers(pda_model* m, float* W_ext, float* G_ext) {
+    if (!m || !W_ext || !G_ext) return fail(PDA_ERR_ARG, "null argument");
+    if (((uintptr_t)W_ext | (uintptr_t)G_ext) & 15) return fail(PDA_ERR_ARG, "buffers must be 16-byte aligned");
+    CK(cudaSetDevice(m->cfg.device));
+    flush_lazy(m, 0);
+    CK(cudaDeviceSynchronize());
+    const size_t bytes = (size_t)m->n4[1] * 16;
+    CK(cudaMemcpy(W_ext, m->W[1], bytes, cudaMemcpyDeviceToDevice));
+    CK(cudaMemcpy(G_ext, m->G[1], bytes, cudaMemcpyDeviceToDevice));
+    if (!m->item_ext) { cudaFree(m->W[1]); cudaFree(m->G[1]); }
+    m->W[1] = W_ext; m->G[1] = G_ext; m->item_ext = 1;
+    return PDA_OK;
+}
+
+// reduce-scatter + sliced Adam + all-gather of the item table in one kernel over NVLink multicast (pda_exchange.cu).
+// mcG / mcW: the MULTICAST addresses of the (adopted) accumulator / table, rows [row_lo, row_hi) = this rank's slice.
+// The caller orders it between two cross-rank barriers on `stream`; the accumulator is left as it is (zero it after
+// the second barrier).
+int pda_dp_exchange_adam(pda_model* m, const float* mcG, float* mcW, int64_t row_lo, int64_t row_hi, void* stream) {
+    if (!m || !mcG || !mcW) return fail(PDA_ERR_ARG, "null argument");
+    if (row_lo < 0 || row_hi > m->nI || row_lo > row_hi) return fail(PDA_ERR_ARG, "row range outside the item table");
+    if (m->adam_lazy[1]) return fail(PDA_ERR_STATE, "the item table is kept lazily: there is no dense sweep to run on it");
+    if (row_lo == row_hi) return PDA_OK;
+    CK(cudaSetDevice(m->cfg.device));
+    const size_t off = (size_t)row_lo * m->d;
+    { ProfScope ps(m, PDA_PROF_ADAM, (cudaStream_t)stream);
+      launch_dp_exchange_adam(mcG + off, mcW + off, m->W[1] + off, m->Mo[1] + off, m->Vo[1] + off, (row_hi - row_lo) * m->d / 4, m->pw,
+                              m->cfg.lr, (cudaStream_t)stream); }
     CK(cudaGetLastError());
     return PDA_OK;
 }

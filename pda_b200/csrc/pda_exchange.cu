@@ -1,0 +1,64 @@
+// Data-parallel item-gradient exchange fused with the optimizer, over NVLink multicast (NVLS):
+//
+//   reduce-scatter  +  TF1 Adam sweep of the rank's row slice  +  all-gather      in ONE kernel.
+//
+// The item-gradient accumulator G and the item table W of every rank live in symmetric memory bound to one multicast
+// object (the caller sets that up: torch.distributed._symmetric_memory in pda_b200/parallel.py).  For its own row slice a
+// rank reads the SUM over all ranks' accumulators with multimem.ld_reduce (the NVSwitch adds in flight: the rank receives
+// one reduced copy, 1/world of the table), applies the Adam update of MF/model_api.py:83 (AdamOptimizer._apply_sparse_
+// shared: the dense form, same separately rounded fp32 operations as adam_dense_kernel) to its slice of W, m, v, and
+// writes the new rows to EVERY replica with multimem.st (one store, multicast by the switch).  Per rank and step
+// (n_items x d fp32 = S bytes): sent (7/8 + 1/8) S, received (1/8 + 7/8) S, both directions busy at the same time --
+// against (7/8 + 7/8) S each way for a reduce-scatter followed by an all-gather.
+// Every element is reduced once, by its owner, and broadcast: the replicas stay bit-identical.
+// Ordering: the caller brackets the kernel with two cross-rank barriers on the same stream (all step kernels done before
+// the first read; all replicas written and all accumulators read before anything overwrites them).
+#include "../../include/pda_b200.h"
+#include "pda_kernels.h"
+
+namespace pda {
+
+__device__ __forceinline__ float4 multimem_ld_reduce_add(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+__device__ __forceinline__ void multimem_st(float* mc, const float4& v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__device__ __forceinline__ void adam_elem_x(float& w, float& m, float& v, float g, float lr_t) {
+    const float omb1 = fsub(1.0f, 0.9f), omb2 = fsub(1.0f, 0.999f);
+    m = fadd(fmul(m, 0.9f), fmul(g, omb1));
+    v = fadd(fmul(v, 0.999f), fmul(fmul(g, g), omb2));
+    w = fsub(w, fdiv(fmul(lr_t, m), fadd(fsqrt(v), 1e-8f)));
+}
+
+// mcG / mcW: multicast addresses of the first element of the rank's slice; W, M, V: the local slice; n4 float4s
+__global__ void __launch_bounds__(256) dp_exchange_adam_kernel(const float* __restrict__ mcG, float* __restrict__ mcW,
+                                                               const float* __restrict__ W, float* __restrict__ M, float* __restrict__ V,
+                                                               int64_t n4, const float* __restrict__ pw, float lr) {
+    const float lr_t = fdiv(fmul(lr, fsqrt(fsub(1.0f, pw[1]))), fsub(1.0f, pw[0]));
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
+        const float4 g = multimem_ld_reduce_add(mcG + 4 * e);
+        float4 w = reinterpret_cast<const float4*>(W)[e], m = reinterpret_cast<float4*>(M)[e], v = reinterpret_cast<float4*>(V)[e];
+        adam_elem_x(w.x, m.x, v.x, g.x, lr_t);
+        adam_elem_x(w.y, m.y, v.y, g.y, lr_t);
+        adam_elem_x(w.z, m.z, v.z, g.z, lr_t);
+        adam_elem_x(w.w, m.w, v.w, g.w, lr_t);
+        reinterpret_cast<float4*>(M)[e] = m;
+        reinterpret_cast<float4*>(V)[e] = v;
+        multimem_st(mcW + 4 * e, w);          // every replica, this rank's included
+    }
+}
+
+void launch_dp_exchange_adam(const float* mcG, float* mcW, const float* W, float* M, float* V, int64_t n4, const float* pw,
+                             float lr, cudaStream_t st) {
+    int64_t blocks = (n4 + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    dp_exchange_adam_kernel<<<(int)blocks, 256, 0, st>>>(mcG, mcW, W, M, V, n4, pw, lr);
+}
+
+}  // namespace pda

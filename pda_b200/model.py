@@ -283,6 +283,15 @@ class PDAModel:
         check(self.lib.pda_adam_dense_rows_ext(self._h, self._TABLES[name], int(row_lo), int(row_hi), ptr(int(grad_ptr)),
                                                ptr(stream) if stream else None))
 
+    def adopt_item_buffers(self, W_ptr, G_ptr):
+        """item table + item-gradient accumulator move into caller-owned device memory (symmetric / multicast-mapped)"""
+        check(self.lib.pda_adopt_item_buffers(self._h, ptr(int(W_ptr)), ptr(int(G_ptr))))
+
+    def dp_exchange_adam(self, mc_G, mc_W, row_lo, row_hi, stream=0):
+        """reduce-scatter + sliced Adam + all-gather of the item table in one NVLink-multicast kernel (pda_exchange.cu)"""
+        check(self.lib.pda_dp_exchange_adam(self._h, ptr(int(mc_G)), ptr(int(mc_W)), int(row_lo), int(row_hi),
+                                            ptr(stream) if stream else None))
+
     def stage_batch_async(self, users, pos_items, neg_items, pos_pop=None, neg_pop=None, copy_stream=0):
         """enqueue the host->device copies (+ the id / distinct-users check) of a PINNED host batch on `copy_stream` and
         return; staged_batch_wait() completes it.  The arrays must stay alive until then."""

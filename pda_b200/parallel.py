@@ -62,8 +62,9 @@ class ShardedTrainer:
         self._zero_pending = False
         self._pending = []
         self.nch = 1
-        exchange = exchange or os.environ.get("PDA_DP_EXCHANGE", "scatter")
+        exchange = exchange or os.environ.get("PDA_DP_EXCHANGE", "auto")     # auto: nvls where available, else scatter
         self.exchange = exchange
+        self._nvls = None
         if int(world) > 1 and getattr(model, "train", "") == "temp_pop":
             raise NotImplementedError("data-parallel training covers BPRMF / PD / PDG (the bias tables of BPR(t)-pop are not exchanged)")
         self._gi = self._acc = None
@@ -81,7 +82,7 @@ class ShardedTrainer:
                 self._reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
                 if hasattr(model, "adam_dense_rows_ext"):     # split optimizer available: asynchronous work handles
                     self._async_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
-            scatter_ok = exchange == "scatter" and self._async_reduce is not None and model.n_items % self.world == 0
+            scatter_ok = exchange in ("scatter", "auto", "nvls") and self._async_reduce is not None and model.n_items % self.world == 0
             if hasattr(model, "exchange_tensors"):     # host stand-ins (tests) hand their buffers over directly
                 ex = model.exchange_tensors()
                 self._gi, self._acc = ex[0], ex[1]
@@ -96,12 +97,23 @@ class ShardedTrainer:
                     self._wi = torch.as_tensor(_DevArray(model.table_ptr("item_embedding"), (model.n_items, model.emb_dim),
                                                          "<f4"), device=dev)
                 self._side, self._zs, self._copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-            if self._wi is not None:
+                if scatter_ok and exchange in ("auto", "nvls"):
+                    self._nvls = self._setup_nvls(dev)
+                    if self._nvls is None and exchange == "nvls":
+                        raise RuntimeError("exchange='nvls' requested but NVLink multicast (symmetric memory) is not available")
+            if self._nvls is not None:
+                rows = model.n_items // self.world
+                self.nch = 1
+                self._own = [(self.rank * rows, (self.rank + 1) * rows)]
+                self._chunk = [(0, model.n_items)]
+                self.exchange = "nvls"
+            elif self._wi is not None:
+                self.exchange = "scatter"
                 # The exchange runs in `nch` row chunks; inside chunk c (rows [c R, (c+1) R), R = n_items / nch) rank r
                 # owns rows [c R + r R/world, c R + (r+1) R/world).  Reduce-scatter of chunk c+1 (send-heavy with in-switch
                 # reduction) and all-gather of chunk c (receive-heavy with multicast) travel on two communicators and
                 # overlap; so does the sliced Adam sweep.
-                nch = int(os.environ.get("PDA_DP_CHUNKS", "4"))
+                nch = int(os.environ.get("PDA_DP_CHUNKS", "2"))     # measured at 8 GPUs: 1 -> 2.96, 2 -> 2.92, 4 -> 2.94, 8 -> 3.12 ms/step
                 while nch > 1 and model.n_items % (nch * self.world) != 0:
                     nch -= 1
                 self.nch = nch
@@ -118,6 +130,40 @@ class ShardedTrainer:
                     except Exception:
                         self._pg_ag = dist.new_group(backend="nccl")
         self._prof = None
+
+    def _setup_nvls(self, dev):
+        """item table + item-gradient accumulator into symmetric memory with a multicast mapping (torch plumbing); None when
+        the platform has no NVLink multicast.  Collective: every rank calls it."""
+        import torch
+        import torch.distributed as dist
+        m = self.model
+        n = m.n_items * m.emb_dim
+        ok, st = 1, None
+        try:
+            import torch.distributed._symmetric_memory as symm
+            try:
+                symm.enable_symm_mem_for_group(dist.group.WORLD.group_name)
+            except Exception:
+                pass
+            buf = symm.empty(2 * n, dtype=torch.float32, device=dev)
+            hdl = symm.rendezvous(buf, dist.group.WORLD)
+            mc = int(hdl.multicast_ptr)
+            if mc == 0:
+                ok = 0
+            st = dict(buf=buf, hdl=hdl, mcW=mc, mcG=mc + 4 * n)
+        except Exception as e:      # no symmetric memory on this platform / torch build
+            import sys
+            print("pda_b200: NVLink multicast exchange unavailable (%r); using the NCCL exchange" % (e,), file=sys.stderr)
+            ok = 0
+        flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            return None
+        buf = st["buf"]
+        m.adopt_item_buffers(buf.data_ptr(), buf.data_ptr() + 4 * n)
+        self._wi = buf[:n].view(m.n_items, m.emb_dim)
+        self._gi = buf[n:].view(m.n_items, m.emb_dim)
+        return st
 
     # ---- stream plumbing: the library enqueues on the raw `stream`; torch (NCCL, memsets) must order against the same one
     def _cs(self, stream):
@@ -154,7 +200,9 @@ class ShardedTrainer:
         torch.cuda.synchronize()
         p = self._prof
         n = min(len(p["fwd"]), len(p["rs"]), len(p["adam"]), len(p["ag"]))
-        out = {"steps": n, "chunks": self.nch, "two_communicators": self._pg_ag is not None}
+        out = {"steps": n, "exchange": self.exchange, "chunks": self.nch, "two_communicators": getattr(self, "_pg_ag", None) is not None}
+        if self.exchange == "nvls":
+            out["phases"] = "rs_exposed = barrier + fused multimem kernel, adam_after_rs = second barrier, ag_exposed = accumulator memset"
         out["rs_exposed_ms"] = sum(p["fwd"][i].elapsed_time(p["rs"][i]) for i in range(n)) / n
         out["adam_after_rs_ms"] = sum(p["rs"][i].elapsed_time(p["adam"][i]) for i in range(n)) / n
         out["ag_exposed_ms"] = sum(p["adam"][i].elapsed_time(p["ag"][i]) for i in range(n)) / n
@@ -172,6 +220,23 @@ class ShardedTrainer:
         if self._async_reduce is None:
             self._exchange()
             m.adam_apply(stream)
+            return
+        if self._nvls is not None:
+            # reduce-scatter + sliced Adam + all-gather in ONE kernel over NVLink multicast (pda_exchange.cu), bracketed by
+            # two cross-rank barriers on the compute stream (symmetric-memory signal pads)
+            h = self._nvls["hdl"]
+            wacc = self._async_reduce(self._acc)
+            m.adam_apply(stream, part=1)
+            h.barrier(channel=0)                  # every rank's step kernel is done: the accumulators are complete
+            lo, hi = self._own[0]
+            m.dp_exchange_adam(self._nvls["mcG"], self._nvls["mcW"], lo, hi, stream)
+            self._mark("rs")
+            h.barrier(channel=1)                  # every replica written, every accumulator read
+            self._mark("adam")
+            self._gi.zero_()
+            self._mark("ag")
+            wacc.wait()
+            m.adam_apply(stream, part=8)
             return
         if self._own is not None:
             import torch.distributed as dist

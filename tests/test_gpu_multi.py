@@ -39,7 +39,9 @@ def _worker(rank, world, port, q, adam_mode, exchange):
         m.set_table("item_embedding", I)
         if adam_mode == "lazy":
             m.set_adam_mode("lazy")       # the trainer narrows it to lazy users + dense (all-reduced) items
-        tr = ShardedTrainer(m, world, rank, exchange=exchange)
+        tr = ShardedTrainer(m, world, rank, exchange=exchange)     # "auto": the fused NVLink-multicast kernel where available
+        if rank == 0:
+            print("exchange used:", tr.exchange, file=sys.stderr)
         stream = torch.cuda.current_stream().cuda_stream
         losses = []
         for step in range(6):
@@ -60,7 +62,7 @@ def _worker(rank, world, port, q, adam_mode, exchange):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("adam_mode,exchange", [("dense", "scatter"), ("lazy", "scatter"), ("lazy", "allreduce")])
+@pytest.mark.parametrize("adam_mode,exchange", [("dense", "scatter"), ("lazy", "scatter"), ("lazy", "allreduce"), ("lazy", "auto")])
 def test_two_gpus_equal_one_process_on_the_union_batch(c_oracle, adam_mode, exchange):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
