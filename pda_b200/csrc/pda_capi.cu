@@ -739,7 +739,7 @@ int pda_dp_exchange_adam(pda_model* m, const float* mcG, float* mcW, int64_t row
     CK(cudaSetDevice(m->cfg.device));
     const size_t off = (size_t)row_lo * m->d;
     { ProfScope ps(m, PDA_PROF_ADAM, (cudaStream_t)stream);
-      launch_dp_exchange_adam(mcG + off, mcW + off, m->W[1] + off, m->Mo[1] + off, m->Vo[1] + off, (row_hi - row_lo) * m->d / 4, m->pw,
+      launch_dp_exchange_adam(mcG + off, mcW + off, m->G[1] + off, m->W[1] + off, m->Mo[1] + off, m->Vo[1] + off, (row_hi - row_lo) * m->d / 4, m->pw,
                               m->cfg.lr, (cudaStream_t)stream); }
     CK(cudaGetLastError());
     return PDA_OK;

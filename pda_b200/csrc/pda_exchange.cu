@@ -13,6 +13,8 @@
 // Every element is reduced once, by its owner, and broadcast: the replicas stay bit-identical.
 // Ordering: the caller brackets the kernel with two cross-rank barriers on the same stream (all step kernels done before
 // the first read; all replicas written and all accumulators read before anything overwrites them).
+#include <stdlib.h>
+
 #include "../../include/pda_b200.h"
 #include "pda_kernels.h"
 
@@ -35,30 +37,57 @@ __device__ __forceinline__ void adam_elem_x(float& w, float& m, float& v, float 
     w = fsub(w, fdiv(fmul(lr_t, m), fadd(fsqrt(v), 1e-8f)));
 }
 
-// mcG / mcW: multicast addresses of the first element of the rank's slice; W, M, V: the local slice; n4 float4s
+// mcG / mcW: multicast addresses of the first element of the rank's slice; W, M, V: the local slice; n4 float4s.
+// U float4s per thread and iteration: all multimem loads of an iteration are in flight before the first is consumed.
+// dbg (tuning only, results are wrong unless 3): bit 0 = read the accumulator through the multicast address (else the
+// local replica), bit 1 = write the table through the multicast address (else the local replica).
+template <int U>
 __global__ void __launch_bounds__(256) dp_exchange_adam_kernel(const float* __restrict__ mcG, float* __restrict__ mcW,
-                                                               const float* __restrict__ W, float* __restrict__ M, float* __restrict__ V,
-                                                               int64_t n4, const float* __restrict__ pw, float lr) {
+                                                               const float* __restrict__ Gl, float* __restrict__ W, float* __restrict__ M,
+                                                               float* __restrict__ V, int64_t n4, const float* __restrict__ pw, float lr,
+                                                               int dbg) {
     const float lr_t = fdiv(fmul(lr, fsqrt(fsub(1.0f, pw[1]))), fsub(1.0f, pw[0]));
-    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < n4; e += (int64_t)gridDim.x * blockDim.x) {
-        const float4 g = multimem_ld_reduce_add(mcG + 4 * e);
-        float4 w = reinterpret_cast<const float4*>(W)[e], m = reinterpret_cast<float4*>(M)[e], v = reinterpret_cast<float4*>(V)[e];
-        adam_elem_x(w.x, m.x, v.x, g.x, lr_t);
-        adam_elem_x(w.y, m.y, v.y, g.y, lr_t);
-        adam_elem_x(w.z, m.z, v.z, g.z, lr_t);
-        adam_elem_x(w.w, m.w, v.w, g.w, lr_t);
-        reinterpret_cast<float4*>(M)[e] = m;
-        reinterpret_cast<float4*>(V)[e] = v;
-        multimem_st(mcW + 4 * e, w);          // every replica, this rank's included
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n4; base += stride) {
+        float4 g[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t e = base + (int64_t)u * blockDim.x;
+            if (e < n4) g[u] = (dbg & 1) ? multimem_ld_reduce_add(mcG + 4 * e) : reinterpret_cast<const float4*>(Gl)[e];
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int64_t e = base + (int64_t)u * blockDim.x;
+            if (e >= n4) continue;
+            float4 w = reinterpret_cast<const float4*>(W)[e], m = reinterpret_cast<float4*>(M)[e], v = reinterpret_cast<float4*>(V)[e];
+            adam_elem_x(w.x, m.x, v.x, g[u].x, lr_t);
+            adam_elem_x(w.y, m.y, v.y, g[u].y, lr_t);
+            adam_elem_x(w.z, m.z, v.z, g[u].z, lr_t);
+            adam_elem_x(w.w, m.w, v.w, g[u].w, lr_t);
+            reinterpret_cast<float4*>(M)[e] = m;
+            reinterpret_cast<float4*>(V)[e] = v;
+            if (dbg & 2) multimem_st(mcW + 4 * e, w);          // every replica, this rank's included
+            else reinterpret_cast<float4*>(W)[e] = w;
+        }
     }
 }
 
-void launch_dp_exchange_adam(const float* mcG, float* mcW, const float* W, float* M, float* V, int64_t n4, const float* pw,
-                             float lr, cudaStream_t st) {
-    int64_t blocks = (n4 + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
+static int env_i(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+void launch_dp_exchange_adam(const float* mcG, float* mcW, const float* Gl, float* W, float* M, float* V, int64_t n4,
+                             const float* pw, float lr, cudaStream_t st) {
+    const int U = env_i("PDA_DPX_UNROLL", 4), dbg = env_i("PDA_DPX_DBG", 3);
+    int64_t blocks = (n4 + 256 * U - 1) / (256 * U);
+    const int cap = env_i("PDA_DPX_BLOCKS", 148 * 4);
+    if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    dp_exchange_adam_kernel<<<(int)blocks, 256, 0, st>>>(mcG, mcW, W, M, V, n4, pw, lr);
+    if (U == 1) dp_exchange_adam_kernel<1><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg);
+    else if (U == 2) dp_exchange_adam_kernel<2><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg);
+    else if (U == 8) dp_exchange_adam_kernel<8><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg);
+    else dp_exchange_adam_kernel<4><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg);
 }
 
 }  // namespace pda

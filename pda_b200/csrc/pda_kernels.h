@@ -84,8 +84,8 @@ int launch_bpr_step_pipe(const StepArgs& a, cudaStream_t st);   // pda_step_pipe
 void launch_adam_dense(const AdamArgs& a, cudaStream_t st);
 void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float* pw, int64_t B, float regs,
                         int batch_size, int advance_powers, float lr, float* lr_slot, cudaStream_t st);
-void launch_dp_exchange_adam(const float* mcG, float* mcW, const float* W, float* M, float* V, int64_t n4, const float* pw,
-                             float lr, cudaStream_t st);   // pda_exchange.cu
+void launch_dp_exchange_adam(const float* mcG, float* mcW, const float* Gl, float* W, float* M, float* V, int64_t n4,
+                             const float* pw, float lr, cudaStream_t st);   // pda_exchange.cu
 int launch_adam_lazy_rows(const LazyArgs& a, int phase, cudaStream_t st);
 void launch_adam_lazy_flush(const LazyArgs& a, int tbl, int64_t n_rows, cudaStream_t st);
 void launch_batch_check(const int32_t* users, const int32_t* pos, const int32_t* neg, int64_t B, int32_t n_users,
