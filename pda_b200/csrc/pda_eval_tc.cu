@@ -292,6 +292,38 @@ __global__ void __launch_bounds__(256) tc_tile_top2_kernel(const float* __restri
     if (lane == 0) { t1[t] = fmaxf(m1, 0.f); targ[t] = j1; t2[t] = fmaxf(m2, 0.f); }
 }
 
+// The tiles with the largest pops, sorted descending (value, then ascending tile id): out_val / out_id [cap].  One block,
+// bitonic sort of all tile keys in shared memory (n_tiles <= HOT_SORT_MAX).  The rescoring stage finds the tiles whose
+// largest pop reaches a row's tau as a PREFIX of this list instead of scanning all tiles for every row.
+constexpr int HOT_SORT_MAX = 16384;
+__global__ void __launch_bounds__(1024) tc_tile_hot_kernel(const float* __restrict__ tcol, int n_tiles, int cap, float* __restrict__ out_val,
+                                                           int32_t* __restrict__ out_id) {
+    extern __shared__ unsigned long long hot_keys[];
+    int n2 = 1024;
+    while (n2 < n_tiles) n2 <<= 1;
+    for (int i = threadIdx.x; i < n2; i += 1024)
+        hot_keys[i] = i < n_tiles ? ((unsigned long long)__float_as_uint(fmaxf(tcol[i], 0.f)) << 32) | (uint32_t)(0x7fffffff - i) : 0ull;
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int idx = threadIdx.x; idx < n2; idx += 1024) {
+                const int ixj = idx ^ j;
+                if (ixj > idx) {
+                    const unsigned long long x = hot_keys[idx], y = hot_keys[ixj];
+                    const bool desc = (idx & k) == 0;
+                    if (desc ? x < y : x > y) { hot_keys[idx] = y; hot_keys[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < cap; i += 1024) {
+        const unsigned long long kv = i < n_tiles ? hot_keys[i] : 0ull;
+        out_val[i] = i < n_tiles ? __uint_as_float((uint32_t)(kv >> 32)) : -1.0f;
+        out_id[i] = i < n_tiles ? 0x7fffffff - (int32_t)(uint32_t)(kv & 0xffffffffu) : 0;
+    }
+}
+
 // Pass A does not sample every se-th tile blindly: it takes the n_sel tiles whose items can score highest for ANY user --
 // key = max |w_j| + max |x_j| of the tile (large item norms / popularities: the usual MIPS "norm ranging" heuristic).
 // Their chunk maxima give a tau much closer to the true K-th best than a uniform sample of the same size, so the full
@@ -888,6 +920,8 @@ struct RescoreArgs {
     int rc;             // per-row capacity of the compacted candidate list (multiple of 32, <= 2048)
     // mode 1, the pop branch of the upper bound: per 128-item tile the largest pop, its item, the second largest
     const float* tile_col; const int32_t* tile_arg; const float* tile_col2; int n_tiles;
+    // the HOT_CAP tiles with the largest pops, sorted descending (tc_tile_hot_kernel); n_hot_sorted = 0: not available
+    const float* hot_val; const int32_t* hot_id; int n_hot_sorted;
     int32_t* clist;     // [M][rc] unmasked candidate ids of the row
     uint32_t* ckeys;    // [M][rc] order-preserving keys of their exact transformed scores
     int32_t* ccount;    // [M] entries of clist, -1 = the row cannot be certified (overflow)
@@ -976,18 +1010,31 @@ __global__ void __launch_bounds__(128) tc_collect_kernel(RescoreArgs a) {
     if (a.mode == 1) {
         const float tl = tc::tau_lower(a.tau[row]);
         int n_hot = 0;
-        for (int tb = 0; tb < a.n_tiles; tb += 128) {
-            bool h[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) { const int t = tb + q * 32 + lane; h[q] = t < a.n_tiles && __ldg(a.tile_col + t) >= tl; }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const unsigned bal = __ballot_sync(0xffffffffu, h[q]);
-                if (h[q]) {
-                    const int pos = n_hot + __popc(bal & ((1u << lane) - 1u));
-                    if (pos < HOT_CAP) hot[pos] = tb + q * 32 + lane;
-                }
+        if (a.n_hot_sorted > 0) {
+            // the hot tiles are a prefix of the list sorted by the tile's largest pop
+            for (int i0 = 0; i0 < a.n_hot_sorted; i0 += 32) {
+                const int i = i0 + lane;
+                const bool hh = i < a.n_hot_sorted && __ldg(a.hot_val + i) >= tl;
+                const unsigned bal = __ballot_sync(0xffffffffu, hh);
+                if (hh) hot[i] = __ldg(a.hot_id + i);
                 n_hot += __popc(bal);
+                if (bal != 0xffffffffu) break;
+            }
+            if (n_hot == a.n_hot_sorted && a.n_hot_sorted < a.n_tiles) n_hot = HOT_CAP + 1;     // the list may not hold them all
+        } else {
+            for (int tb = 0; tb < a.n_tiles; tb += 128) {
+                bool h[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { const int t = tb + q * 32 + lane; h[q] = t < a.n_tiles && __ldg(a.tile_col + t) >= tl; }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const unsigned bal = __ballot_sync(0xffffffffu, h[q]);
+                    if (h[q]) {
+                        const int pos = n_hot + __popc(bal & ((1u << lane) - 1u));
+                        if (pos < HOT_CAP) hot[pos] = tb + q * 32 + lane;
+                    }
+                    n_hot += __popc(bal);
+                }
             }
         }
         if (n_hot > HOT_CAP) { if (lane == 0) a.ccount[row] = -1; return; }
@@ -1268,7 +1315,10 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
         // the sample is the n_tiles / se tiles with the largest norms / pops (tc_tile_select_kernel), far more informative
         // than a blind one: stride 8 halves pass A against 4 for 0-30 % more candidates (measured: 16.3 -> 14.6 ms per
         // 65536 users on the bench set, 4.37 -> 4.01 ms per 16384 on tools/eval_bench.py's)
-        if (se < 8 && env_int("PDA_TC_ORDERED", 1)) se = 8;
+        // r2 sweep (65536 users x 1M items, d = 128): stride 8 / 12 / 16 / 24 -> 14.45 / 13.90 / 13.66 / 13.49 ms on a near-init
+        // model (57 candidates per row at every stride) and 14.80 / 14.56 / 14.67 / 15.40 ms on fitted-like tables (118 /
+        // 165 / 225 / 353 candidates per row): 12 is the balance
+        if (se < 12 && env_int("PDA_TC_ORDERED", 1)) se = 12;
         const int want = env_int("PDA_TC_SE", 0);           // tuning knob
         if (want >= 1 && (int64_t)(p->n_tiles + want - 1) / want * 2 <= TAU_MAX_KEYS) se = want;
     }
@@ -1316,6 +1366,8 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->o_tcol2 = o; o += al256((size_t)p->n_tiles * 4);
     p->o_torder = o; o += al256((size_t)p->n_tiles * 4);
     p->o_tpos = o; o += al256((size_t)p->n_tiles * 4);
+    p->o_hotv = o; o += al256((size_t)HOT_CAP * 4);
+    p->o_hoti = o; o += al256((size_t)HOT_CAP * 4);
     p->o_nflag = o; o += 256;          // [0] rows without a certificate, [1] negative-pop flag
     p->o_Ub = o; o += al256((size_t)p->M_pad * a.d * 2);
     p->o_Ux = o; o += al256((size_t)p->M_pad * KX * 2);
@@ -1390,6 +1442,12 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
                                                                                                  (float*)(b + p.o_tcol2));
         else if (kx)
             tc_tile_max_kernel<<<(unsigned)(((int64_t)p.n_tiles * 32 + 255) / 256), 256, 0, st>>>(xcol, p.n_tiles, tcolmax, a.N);
+        if (a.mode == 1 && p.n_tiles <= HOT_SORT_MAX) {
+            int n2 = 1024;
+            while (n2 < p.n_tiles) n2 <<= 1;
+            if (cudaFuncSetAttribute(tc_tile_hot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, n2 * 8) != cudaSuccess) return 4;
+            tc_tile_hot_kernel<<<1, 1024, (size_t)n2 * 8, st>>>(tcolmax, p.n_tiles, HOT_CAP, (float*)(b + p.o_hotv), (int32_t*)(b + p.o_hoti));
+        }
         if (p.ordered)
             tc_tile_select_kernel<<<1, 1024, 0, st>>>(tnorm, kx ? tcolmax : nullptr, p.n_tiles, p.n_sel, (int32_t*)(b + p.o_torder),
                                                       (int32_t*)(b + p.o_tpos));
@@ -1457,6 +1515,8 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, bool 
     r.tau = tau; r.K = a.K; r.rc = p.rc;
     r.tile_col = s.tile_col; r.tile_arg = (const int32_t*)(b + p.o_targ); r.tile_col2 = (const float*)(b + p.o_tcol2);
     r.n_tiles = p.n_tiles;
+    r.hot_val = (const float*)(b + p.o_hotv); r.hot_id = (const int32_t*)(b + p.o_hoti);
+    r.n_hot_sorted = (a.mode == 1 && p.n_tiles <= HOT_SORT_MAX) ? (p.n_tiles < HOT_CAP ? p.n_tiles : HOT_CAP) : 0;
     r.ids_out = a.ids_out; r.scores_out = a.scores_out; r.flag = flag;
     r.clist = (int32_t*)(b + p.o_clist); r.ckeys = (uint32_t*)(b + p.o_ckeys); r.ccount = (int32_t*)(b + p.o_ccount);
     r.work = (int32_t*)(b + p.o_work); r.n_work = (int32_t*)(b + p.o_nwork);

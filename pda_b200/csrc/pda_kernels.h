@@ -73,7 +73,7 @@ struct EvalArgs {
 struct TcPlan {
     int64_t M_pad, N_pad;
     int n_tiles, mr, ts, ordered, n_sel, se, cw, n_c, n_valid, splits, tiles_per_split, n_seg, seg_cap, rc;
-    size_t o_Ib, o_Ub, o_Ix, o_Ux, o_inorm, o_unorm, o_tnorm, o_tcolmax, o_targ, o_tcol2, o_torder, o_tpos, o_cmax, o_tau, o_cnt, o_cand, o_flag, o_frows, o_fusers, o_nflag, o_clist, o_ckeys, o_ccount, o_work, o_nwork;
+    size_t o_Ib, o_Ub, o_Ix, o_Ux, o_inorm, o_unorm, o_tnorm, o_tcolmax, o_targ, o_tcol2, o_torder, o_tpos, o_hotv, o_hoti, o_cmax, o_tau, o_cnt, o_cand, o_flag, o_frows, o_fusers, o_nflag, o_clist, o_ckeys, o_ccount, o_work, o_nwork;
 };
 
 void launch_xavier_init(float* W, int64_t rows, int cols, uint32_t seed, uint32_t table_id, cudaStream_t st);

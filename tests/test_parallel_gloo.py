@@ -117,6 +117,7 @@ def _worker(rank, world, port, q, exchange="scatter"):
         I = rng.normal(0, 0.3, (n_items, d)).astype(np.float32)
         lo, hi = shard_range(n_users, world, rank)
         model = HostStandIn(U[lo:hi], I, 1e-2, 1e-3, B * world)
+        os.environ["PDA_DP_CHUNKS"] = "4"
         tr = ShardedTrainer(model, world, rank, exchange=exchange)
         assert (tr._own is not None) == (exchange == "scatter")
         assert exchange != "scatter" or tr.nch == 4      # 48 item rows: 4 exchange chunks of 12 rows, 6 per rank
