@@ -107,6 +107,11 @@ int pda_synchronize(pda_model* m);
 #define PDA_ADAM_LAZY 1
 #define PDA_ADAM_LAZY_USERS 2
 int pda_set_adam_mode(pda_model* m, int mode);
+/* Duplicate rows inside a batch (items): TF1 sums them before the optimizer (_deduplicate_indexed_slices behind
+ * MF/model_api.py:83).  Default: fp32 red.global.add in L2 (order not fixed: 1e-5 per step against the oracle).  on != 0:
+ * the per-triple gradient rows are stored and summed in occurrence order (pos slots, then neg slots) -- the whole
+ * trajectory is bit-identical to the CPU oracle, at about twice the step cost.  $PDA_DETERMINISTIC=1 sets it at create. */
+int pda_set_deterministic(pda_model* m, int on);
 /* out[0] = rows updated with a gradient by the lazy apply kernel, out[1] = zero-gradient row-steps replayed, both since
  * the last call with reset != 0 (synchronises the device) */
 int pda_adam_stats(pda_model* m, int64_t* out2, int reset);

@@ -116,7 +116,9 @@ def sample_batch(seed, epoch, step, B, active_users, indptr, items, times, n_ite
 class CModel:
     """Reference-semantics trainer on CPU (dense TF1 Adam), state in numpy arrays."""
 
-    def __init__(self, U, I, lr, regs, batch_size, mode, copy=True):
+    def __init__(self, U, I, lr, regs, batch_size, mode, copy=True, reversed_sum=False):
+        # reversed_sum: duplicate rows summed in the reversed occurrence order -- a second valid fp32 order, for noise bands
+        self._step = "orc_train_step_rev" if reversed_sum else "orc_train_step"
         self.U = np.array(U, dtype=np.float32, order="C") if copy else np.ascontiguousarray(U, dtype=np.float32)
         self.I = np.array(I, dtype=np.float32, order="C") if copy else np.ascontiguousarray(I, dtype=np.float32)
         self.d = self.U.shape[1]
@@ -139,7 +141,7 @@ class CModel:
             pos_pop = np.ascontiguousarray(pos_pop, dtype=np.float32)
             neg_pop = np.ascontiguousarray(neg_pop, dtype=np.float32)
         loss3 = np.zeros(3, dtype=np.float32)
-        lib().orc_train_step(_p(self.U, c_f), _p(self.mU, c_f), _p(self.vU, c_f), _p(self.GU, c_f),
+        getattr(lib(), self._step)(_p(self.U, c_f), _p(self.mU, c_f), _p(self.vU, c_f), _p(self.GU, c_f),
                              C.c_int64(self.U.shape[0]), _p(self.I, c_f), _p(self.mI, c_f),
                              _p(self.vI, c_f), _p(self.GI, c_f), C.c_int64(self.I.shape[0]),
                              C.c_int(self.d), _p(users, c_i32), _p(pos, c_i32), _p(neg, c_i32),

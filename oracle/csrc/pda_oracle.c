@@ -276,6 +276,26 @@ void orc_scatter_add_rows(float* G, int d, const int32_t* idx, const float* rows
     }
 }
 
+/* the same sum in REVERSED occurrence order: a second, equally valid fp32 summation order (TF's unsorted_segment_sum does not
+ * promise one) -- used only to measure the oracle's own noise band (SURVEY 7 "trajectory divergence" (iii)) */
+void orc_scatter_add_rows_rev(float* G, int d, const int32_t* idx, const float* rows, int64_t n) {
+#pragma omp parallel
+    {
+#ifdef _OPENMP
+        int tid = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+        int tid = 0, nt = 1;
+#endif
+        for (int64_t i = n - 1; i >= 0; --i) {
+            int32_t r = idx[i];
+            if (r % nt != tid) continue;
+            float* g = G + (int64_t)r * d;
+            const float* s = rows + i * d;
+            for (int k = 0; k < d; ++k) g[k] = g[k] + s[k];
+        }
+    }
+}
+
 /* ---- a6: TF1 Adam, dense sweep; G is consumed and zeroed ---- */
 void orc_adam_dense(float* W, float* m, float* v, float* G, int64_t n, float lr_t, int zero_g) {
     const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;
@@ -307,6 +327,23 @@ void orc_train_step(float* U, float* mU, float* vU, float* GU, int64_t n_users, 
     orc_scatter_add_rows(GU, d, users, gU, B);
     orc_scatter_add_rows(GI, d, pos, gP, B);
     orc_scatter_add_rows(GI, d, neg, gN, B);
+    float lr_t = orc_lr_t(lr, pw[0], pw[1]);
+    orc_adam_dense(U, mU, vU, GU, n_users * d, lr_t, 1);
+    orc_adam_dense(I, mI, vI, GI, n_items * d, lr_t, 1);
+    pw[0] = pw[0] * 0.9f; pw[1] = pw[1] * 0.999f;
+}
+
+/* the same step with the duplicate rows summed in the reversed order (neg before pos, last occurrence first) */
+void orc_train_step_rev(float* U, float* mU, float* vU, float* GU, int64_t n_users, float* I, float* mI,
+                        float* vI, float* GI, int64_t n_items, int d, const int32_t* users,
+                        const int32_t* pos, const int32_t* neg, const float* pos_pop, const float* neg_pop,
+                        int64_t B, float lr, float regs, int batch_size, int mode, float* gU, float* gP,
+                        float* gN, float* pw, float* loss3) {
+    orc_bpr_forward_backward(U, I, d, users, pos, neg, pos_pop, neg_pop, B, regs, batch_size, mode, gU,
+                             gP, gN, loss3);
+    orc_scatter_add_rows_rev(GU, d, users, gU, B);
+    orc_scatter_add_rows_rev(GI, d, neg, gN, B);
+    orc_scatter_add_rows_rev(GI, d, pos, gP, B);
     float lr_t = orc_lr_t(lr, pw[0], pw[1]);
     orc_adam_dense(U, mU, vU, GU, n_users * d, lr_t, 1);
     orc_adam_dense(I, mI, vI, GI, n_items * d, lr_t, 1);

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "pda_set_adam_powers": (C.c_int, [c_vp, c_vp]),
     "pda_synchronize": (C.c_int, [c_vp]),
     "pda_set_adam_mode": (C.c_int, [c_vp, C.c_int]),
+    "pda_set_deterministic": (C.c_int, [c_vp, C.c_int]),
     "pda_adam_stats": (C.c_int, [c_vp, c_vp, C.c_int]),
     "pda_profile_enable": (C.c_int, [c_vp, C.c_int]),
     "pda_profile_read": (C.c_int, [c_vp, c_vp, c_vp]),

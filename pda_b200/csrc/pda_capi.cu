@@ -50,6 +50,9 @@ struct pda_model {
     cudaEvent_t ev_staged; int staged_pending;   // pda_stage_batch_host_async / pda_staged_batch_wait
     int32_t max_time;                  // largest stage label of the host-validated train CSR (-1: unknown)
     int item_ext;                      // W[1] / G[1] live in caller-owned (symmetric) memory: not freed here
+    // deterministic duplicate-row accumulation (pda_segsum.cu): slot buffer [3 B, d], sort work arrays, cub temp storage
+    int deterministic;
+    void* gslots; size_t gslots_bytes; void* seg_work; size_t seg_work_bytes; void* seg_temp; size_t seg_temp_bytes;
     float* pw;          // {beta1_power, beta2_power}
     double* loss_acc;   // {sum log(sigmoid+1e-10), sum of squares}
     float* loss3;       // device {loss, mf, reg}
@@ -184,6 +187,8 @@ int pda_create(const pda_config* cfg, pda_model** out) {
         m->adam_lazy[1] = big && m->nI > 8 * m->cap;
         const char* e = getenv("PDA_FUSE_USER_ADAM");
         m->fuse_user_adam = e ? atoi(e) : 1;
+        e = getenv("PDA_DETERMINISTIC");
+        m->deterministic = e ? atoi(e) != 0 : 0;
     }
     CK(dmalloc(&m->lr_hist, (size_t)PDA_LR_CAP));
     CK(dmalloc(&m->lazy_stats, 2)); CK(cudaMemset(m->lazy_stats, 0, 16));
@@ -224,6 +229,9 @@ void pda_destroy(pda_model* m) {
     }
     if (m->loss_ring) cudaFreeHost(m->loss_ring);
     if (m->stage_pinned) cudaFreeHost(m->stage_pinned);
+    if (m->gslots) cudaFree(m->gslots);
+    if (m->seg_work) cudaFree(m->seg_work);
+    if (m->seg_temp) cudaFree(m->seg_temp);
     if (m->ev_buf) cudaFree(m->ev_buf);
     if (m->tc_buf) cudaFree(m->tc_buf);
     if (m->ev_pinned) cudaFreeHost(m->ev_pinned);
@@ -373,6 +381,15 @@ int pda_adam_stats(pda_model* m, int64_t* out2, int reset) {
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(out2, m->lazy_stats, 16, cudaMemcpyDeviceToHost));
     if (reset) CK(cudaMemset(m->lazy_stats, 0, 16));
+    return PDA_OK;
+}
+
+// Deterministic accumulation of duplicate rows (items that repeat inside a batch): on = per-triple gradient rows are stored
+// and summed in occurrence order (the oracle's dedup_sum order) instead of reduced with fp32 atomics -- trajectories become
+// bit-identical to the CPU oracle at ~2x the step cost.  BPRMF / PD / PDG (the bias tables of BPR(t)-pop keep atomics).
+int pda_set_deterministic(pda_model* m, int on) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    m->deterministic = on ? 1 : 0;
     return PDA_OK;
 }
 
@@ -561,7 +578,15 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
     m->cur_users = users; m->cur_pos = pos; m->cur_neg = neg; m->cur_B = B;
     // distinct users + lazily kept user table + an Adam step that is certain to follow: the step kernel itself
     // catches the user rows up and applies their update (bpr_step_kernel UMODE 2)
-    m->cur_fused = m->adam_lazy[0] && uniq && will_apply && m->fuse_user_adam;
+    m->cur_fused = m->adam_lazy[0] && uniq && will_apply && m->fuse_user_adam && !m->deterministic;
+    if (m->deterministic) {
+        // per-triple gradient rows go to a slot buffer; pda_segsum.cu sums the slots of each row in occurrence order
+        const size_t n2 = (size_t)2 * B;
+        CK(ensure_dev(&m->gslots, &m->gslots_bytes, (size_t)3 * B * m->d * 4));
+        CK(ensure_dev(&m->seg_work, &m->seg_work_bytes, n2 * 4 * 4));
+        CK(ensure_dev(&m->seg_temp, &m->seg_temp_bytes, segsum_temp_bytes((int64_t)n2) + 256));
+        s.Gslots = (float*)m->gslots;
+    }
     if ((m->adam_lazy[0] && !m->cur_fused) || m->adam_lazy[1]) {   // rows of this batch replay the steps they skipped
         LazyArgs la;
         lazy_args(m, &la);
@@ -584,8 +609,20 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
         s.temp = m->b_time; s.temp_num = m->cfg.temp_num;
         s.ub = m->W[2]; s.ib = m->W[3]; s.Gub = m->G[2]; s.Gib = m->G[3];
     }
-    ProfScope ps(m, PDA_PROF_STEP, st);
-    if (launch_bpr_step(s, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
+    {
+        ProfScope ps(m, PDA_PROF_STEP, st);
+        if (launch_bpr_step(s, st)) return fail(PDA_ERR_ARG, "unsupported embed_size %d", m->d);
+    }
+    if (m->deterministic) {
+        auto bits_of = [](int64_t n) { int b = 1; while (((int64_t)1 << b) < n) ++b; return b; };
+        ProfScope ps(m, PDA_PROF_ADAM_CATCHUP, st);
+        if (launch_segment_sum(pos, neg, B, (const float*)m->gslots, m->d, m->G[1], (int32_t*)m->seg_work, m->seg_temp, m->seg_temp_bytes,
+                               bits_of(m->nI), st))
+            return fail(PDA_ERR_CUDA, "segment sum (items) failed");
+        if (!uniq && launch_segment_sum(users, nullptr, B, (const float*)m->gslots + (size_t)2 * B * m->d, m->d, m->G[0], (int32_t*)m->seg_work,
+                                        m->seg_temp, m->seg_temp_bytes, bits_of(m->nU), st))
+            return fail(PDA_ERR_CUDA, "segment sum (users) failed");
+    }
     return PDA_OK;
 }
 

@@ -34,6 +34,9 @@ struct StepArgs {
     // fused lazy Adam on the user row (UMODE 2): see bpr_step_kernel
     int fuse_user_adam; float* Uw; float* MU; float* VU; int32_t* appliedU; int32_t* stampU;
     const float* lr_hist; const float* pw; float lr; int64_t step_no; unsigned long long* stats;
+    // deterministic mode (pda_segsum.cu): per-triple gradient rows are STORED, slot i = pos row of triple i, B + i = neg
+    // row, 2B + i = user row (only when users may repeat); the ordered segment sum fills GU / GI afterwards
+    float* Gslots;
 };
 
 struct AdamArgs {
@@ -86,6 +89,9 @@ void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float*
                         int batch_size, int advance_powers, float lr, float* lr_slot, cudaStream_t st);
 void launch_dp_exchange_adam(const float* mcG, float* mcW, const float* Gl, float* W, float* M, float* V, int64_t n4,
                              const float* pw, float lr, cudaStream_t st);   // pda_exchange.cu
+size_t segsum_temp_bytes(int64_t n);
+int launch_segment_sum(const int32_t* a, const int32_t* b, int64_t B, const float* rows, int d, float* G, int32_t* work, void* temp,
+                       size_t temp_bytes, int key_bits, cudaStream_t st);   // pda_segsum.cu
 int launch_adam_lazy_rows(const LazyArgs& a, int phase, cudaStream_t st);
 void launch_adam_lazy_flush(const LazyArgs& a, int tbl, int64_t n_rows, cudaStream_t st);
 void launch_batch_check(const int32_t* users, const int32_t* pos, const int32_t* neg, int64_t B, int32_t n_users,

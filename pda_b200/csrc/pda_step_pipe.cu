@@ -324,7 +324,7 @@ static int launch_pipe_dn(const StepArgs& a, int hints, cudaStream_t st) {
 
 // returns 0 when the pipelined kernel took the launch, non-zero when the shape is not its (the caller falls back)
 int launch_bpr_step_pipe(const StepArgs& a, cudaStream_t st) {
-    if (a.d != 128 || !a.uniq_users || a.pop_mode == 2) return 1;
+    if (a.d != 128 || !a.uniq_users || a.pop_mode == 2 || a.Gslots) return 1;
     const char* e = getenv("PDA_STEP_PIPE");
     if (e && atoi(e) == 0) return 1;
     e = getenv("PDA_STEP_PIPE_HINTS");

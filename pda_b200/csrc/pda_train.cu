@@ -272,9 +272,15 @@ __global__ void __launch_bounds__(256) bpr_step_kernel(StepArgs a) {
                         *reinterpret_cast<float4*>(a.MU + (int64_t)iu * a.d + 4 * ch) = mu[c];
                         *reinterpret_cast<float4*>(a.VU + (int64_t)iu * a.d + 4 * ch) = vu[c];
                     } else if (UNIQ) *reinterpret_cast<float4*>(gu + 4 * ch) = du;
+                    else if (a.Gslots) *reinterpret_cast<float4*>(a.Gslots + (2 * a.B + i) * a.d + 4 * ch) = du;
                     else red_add_f4(gu + 4 * ch, du);
-                    red_add_f4(gp + 4 * ch, dpv);
-                    red_add_f4(gn + 4 * ch, dnv);
+                    if (a.Gslots) {      // deterministic mode: rows kept per slot, summed in order by pda_segsum.cu
+                        *reinterpret_cast<float4*>(a.Gslots + i * a.d + 4 * ch) = dpv;
+                        *reinterpret_cast<float4*>(a.Gslots + (a.B + i) * a.d + 4 * ch) = dnv;
+                    } else {
+                        red_add_f4(gp + 4 * ch, dpv);
+                        red_add_f4(gn + 4 * ch, dnv);
+                    }
                 }
             }
             if (FUSE && gl == 0) { a.appliedU[iu] = (int32_t)(a.step_no + 1); a.stampU[iu] = 1; }

@@ -79,6 +79,11 @@ class PDAModel:
         'lazy_users': lazy user table + dense item table (data-parallel item-gradient all-reduce)."""
         check(self.lib.pda_set_adam_mode(self._h, self.ADAM_MODES[mode]))
 
+    def set_deterministic(self, on=True):
+        """duplicate item rows of a batch summed in occurrence order instead of with fp32 atomics: trajectories
+        bit-identical to the CPU oracle (about twice the step cost)"""
+        check(self.lib.pda_set_deterministic(self._h, 1 if on else 0))
+
     def adam_stats(self, reset=True):
         """(rows updated with a gradient, zero-gradient row-steps replayed) by the lazy Adam kernels since the last reset."""
         out = np.zeros(2, dtype=np.int64)

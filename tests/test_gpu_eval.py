@@ -263,8 +263,8 @@ def test_recommend_tensor_large_item_set_sampled_pass(pda, c_oracle, rec_type, m
         cands[ordered] = st["candidates"]
     print("candidates ordered / blind:", cands)
     assert cands["1"] <= cands["0"] * 1.05
-    monkeypatch.delenv("PDA_TC_SE")                  # the default stride (8 with the ordered sample)
+    monkeypatch.delenv("PDA_TC_SE")                  # the default stride (12 with the ordered sample)
     monkeypatch.setenv("PDA_TC_ORDERED", "1")
     ids = m.do_recommendation(users, None, rec_type, pos_pop=pop, K=K, backend="tensor")
-    assert np.array_equal(ids, rid) and m.tc_last_stats()["tile_stride"] == 8
+    assert np.array_equal(ids, rid) and m.tc_last_stats()["tile_stride"] == 12
     m.close()

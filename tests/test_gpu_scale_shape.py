@@ -1,5 +1,5 @@
 """Parity at the shapes bench.py measures ("prove parity where you benchmark"): d = 128, 1 M items,
-> 32768 eval users (two user blocks: the second one reuses the prepared item operands), stride-8 ordered pass A, 9 item
+> 32768 eval users (two user blocks: the second one reuses the prepared item operands), ordered pass A at the default stride, 9+ item
 splits; and the fused lazy-Adam step kernel at B = 2^20 distinct users against the dense sweep.
 Reference: MF/train_new_api.py:594-612 (scoring), MF/model_api.py:102-121,83 (step + Adam)."""
 import numpy as np
@@ -47,7 +47,7 @@ def test_eval_at_bench_shape_matches_oracle_and_exact_backend(pda, c_oracle, tab
     st = m.tc_last_stats()
     plan = np.zeros(24, dtype=np.int64)
     assert pda.load().pda_tc_plan_host(32768, n_items, d, K, plan.ctypes.data) == 0
-    assert plan[5] == 1 and plan[7] == 8 and plan[11] == 9, plan       # ordered pass A, stride 8, 9 item splits
+    assert plan[5] == 1 and plan[7] == 12 and plan[11] >= 9, plan      # ordered pass A, stride 12, >= 9 item splits
     eid, esc = m.do_recommendation(users, None, "condition", pos_pop=pop, K=K, backend="exact", return_scores=True)
     assert np.array_equal(ids, eid), (tables, st, int((ids != eid).any(axis=1).sum()))
     assert np.array_equal(bits(sc), bits(esc))
