@@ -267,6 +267,18 @@ int pda_metrics_host(pda_model* m, const int32_t* ids, int64_t M, int Kkeep, con
                      const int64_t* truth_indptr, const int32_t* truth_items, int64_t n_truth_rows, const int32_t* Ks,
                      int nK, double* out);
 
+/* NeuRec-style native evaluator entry points over the GPU (the reference's optional native FFI; both stateless, device 0):
+ *   pda_arg_top_k_2d_host    = arg_top_k_2d (util/cython/include/arg_topk.h:29): results int32 [rows, top_k], the indices of
+ *                              the top_k largest scores of every row of the C-contiguous float32 matrix scores[rows, cols],
+ *                              best first; equal scores: lower index first.  top_k <= 128.
+ *   pda_evaluate_matrix_host = cpp_evaluate_matrix (evaluator/backend/cpp/include/evaluate.h:53): per user the top_k of its
+ *                              rating row, then for every requested metric (1 Precision, 2 Recall, 3 MAP, 4 NDCG, 5 MRR;
+ *                              metric.h:109-114) its value at cut-offs 1..top_k -> results float32 [n_users, n_metric * top_k].
+ *                              The reference's vector<unordered_set<int>> of test items is passed as a CSR over users. */
+int pda_arg_top_k_2d_host(const float* scores, int32_t cols, int32_t rows, int32_t top_k, int32_t* results);
+int pda_evaluate_matrix_host(const float* rating_matrix, int32_t rating_len, int32_t n_users, const int64_t* truth_indptr,
+                             const int32_t* truth_items, const int32_t* metric, int32_t n_metric, int32_t top_k, float* results);
+
 /* diagnostics behind the bit-exactness claims of the exact Adam replay: runs a check kernel on the current device and
  * returns out5 = {operands checked, mismatching results, first mismatch: 3 raw words}.
  *   kind 3: every fp32 bit pattern in [lo_or_seed, hi] through the straight-line sqrt refinement vs __fsqrt_rn

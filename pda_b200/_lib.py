@@ -85,6 +85,8 @@ PROTOTYPES = {
     "pda_tc_plan_host": (C.c_int, [C.c_int64, C.c_int64, C.c_int32, C.c_int32, c_vp]),
     "pda_tc_debug_dense_host": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_vp, c_vp, c_vp, c_vp]),
     "pda_scores_host": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_vp, c_vp]),
+    "pda_arg_top_k_2d_host": (C.c_int, [c_vp, C.c_int32, C.c_int32, C.c_int32, c_vp]),
+    "pda_evaluate_matrix_host": (C.c_int, [c_vp, C.c_int32, C.c_int32, c_vp, c_vp, c_vp, C.c_int32, C.c_int32, c_vp]),
     "pda_debug_numerics": (C.c_int, [C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, c_vp]),
     "pda_metrics_host": (C.c_int, [c_vp, c_vp, C.c_int64, C.c_int, c_vp, c_vp, c_vp, C.c_int64, c_vp, C.c_int, c_vp]),
 }

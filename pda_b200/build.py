@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 OUT = os.path.join(HERE, "libpda_b200.so")
 SOURCES = ["pda_capi.cu", "pda_train.cu", "pda_step_pipe.cu", "pda_adam_lazy.cu", "pda_eval_exact.cu", "pda_eval_tc.cu",
-           "pda_exchange.cu", "pda_segsum.cu", "pda_debug.cu"]
+           "pda_exchange.cu", "pda_segsum.cu", "pda_neurec.cu", "pda_debug.cu"]
 HEADERS = ["pda_common.cuh", "pda_kernels.h", os.path.join("..", "..", "include", "pda_b200.h")]
 CC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
             "-Xcompiler", "-O2"]
