@@ -204,6 +204,8 @@ int pda_adam_dense_rows_ext(pda_model* m, int which, int64_t row_lo, int64_t row
  * (multimem.ld_reduce sums the accumulators of all ranks in the switch, multimem.st writes the updated rows to every
  * replica).  The caller brackets it with two cross-rank barriers on `stream` and zeroes the accumulator afterwards. */
 int pda_adopt_item_buffers(pda_model* m, float* W_ext, float* G_ext);
+/* switch the accumulator to another caller-owned ZERO-filled buffer (double buffering; after pda_adopt_item_buffers) */
+int pda_set_item_grad_buffer(pda_model* m, float* G_ext);
 int pda_dp_exchange_adam(pda_model* m, const float* mcG, float* mcW, int64_t row_lo, int64_t row_hi, void* stream);
 int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                          const float* pos_pop, const float* neg_pop, int64_t B, void* stream);

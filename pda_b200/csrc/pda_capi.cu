@@ -764,6 +764,16 @@ int pda_adopt_item_buffers(pda_model* m, float* W_ext, float* G_ext) {
     return PDA_OK;
 }
 
+// Point the item-gradient accumulator at another caller-owned, ZERO-filled [n_items, d] buffer (double buffering: the
+// previous one is zeroed off the critical path while the next step accumulates into this one).
+int pda_set_item_grad_buffer(pda_model* m, float* G_ext) {
+    if (!m || !G_ext) return fail(PDA_ERR_ARG, "null argument");
+    if (!m->item_ext) return fail(PDA_ERR_STATE, "pda_adopt_item_buffers has not been called");
+    if ((uintptr_t)G_ext & 15) return fail(PDA_ERR_ARG, "buffer must be 16-byte aligned");
+    m->G[1] = G_ext;
+    return PDA_OK;
+}
+
 // reduce-scatter + sliced Adam + all-gather of the item table in one kernel over NVLink multicast (pda_exchange.cu).
 // mcG / mcW: the MULTICAST addresses of the (adopted) accumulator / table, rows [row_lo, row_hi) = this rank's slice.
 // The caller orders it between two cross-rank barriers on `stream`; the accumulator is left as it is (zero it after

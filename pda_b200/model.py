@@ -292,6 +292,9 @@ class PDAModel:
         """item table + item-gradient accumulator move into caller-owned device memory (symmetric / multicast-mapped)"""
         check(self.lib.pda_adopt_item_buffers(self._h, ptr(int(W_ptr)), ptr(int(G_ptr))))
 
+    def set_item_grad_buffer(self, G_ptr):
+        check(self.lib.pda_set_item_grad_buffer(self._h, ptr(int(G_ptr))))
+
     def dp_exchange_adam(self, mc_G, mc_W, row_lo, row_hi, stream=0):
         """reduce-scatter + sliced Adam + all-gather of the item table in one NVLink-multicast kernel (pda_exchange.cu)"""
         check(self.lib.pda_dp_exchange_adam(self._h, ptr(int(mc_G)), ptr(int(mc_W)), int(row_lo), int(row_hi),

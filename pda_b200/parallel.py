@@ -145,12 +145,12 @@ class ShardedTrainer:
                 symm.enable_symm_mem_for_group(dist.group.WORLD.group_name)
             except Exception:
                 pass
-            buf = symm.empty(2 * n, dtype=torch.float32, device=dev)
+            buf = symm.empty(3 * n, dtype=torch.float32, device=dev)      # [W | G0 | G1]: the accumulator is double-buffered
             hdl = symm.rendezvous(buf, dist.group.WORLD)
             mc = int(hdl.multicast_ptr)
             if mc == 0:
                 ok = 0
-            st = dict(buf=buf, hdl=hdl, mcW=mc, mcG=mc + 4 * n)
+            st = dict(buf=buf, hdl=hdl, mcW=mc, mcG=[mc + 4 * n, mc + 8 * n], cur=0)
         except Exception as e:      # no symmetric memory on this platform / torch build
             import sys
             print("pda_b200: NVLink multicast exchange unavailable (%r); using the NCCL exchange" % (e,), file=sys.stderr)
@@ -160,9 +160,12 @@ class ShardedTrainer:
         if int(flag.item()) == 0:
             return None
         buf = st["buf"]
+        buf[n:].zero_()
+        torch.cuda.synchronize()
         m.adopt_item_buffers(buf.data_ptr(), buf.data_ptr() + 4 * n)
         self._wi = buf[:n].view(m.n_items, m.emb_dim)
-        self._gi = buf[n:].view(m.n_items, m.emb_dim)
+        st["G"] = [buf[n:2 * n].view(m.n_items, m.emb_dim), buf[2 * n:].view(m.n_items, m.emb_dim)]
+        self._gi = st["G"][0]
         return st
 
     # ---- stream plumbing: the library enqueues on the raw `stream`; torch (NCCL, memsets) must order against the same one
@@ -202,7 +205,8 @@ class ShardedTrainer:
         n = min(len(p["fwd"]), len(p["rs"]), len(p["adam"]), len(p["ag"]))
         out = {"steps": n, "exchange": self.exchange, "chunks": self.nch, "two_communicators": getattr(self, "_pg_ag", None) is not None}
         if self.exchange == "nvls":
-            out["phases"] = "rs_exposed = barrier + fused multimem kernel, adam_after_rs = second barrier, ag_exposed = accumulator memset"
+            out["phases"] = ("rs_exposed = barrier + fused multimem kernel (the other accumulator is zeroed under it), "
+                             "adam_after_rs = second barrier, ag_exposed = 0 (nothing left on the critical path)")
         out["rs_exposed_ms"] = sum(p["fwd"][i].elapsed_time(p["rs"][i]) for i in range(n)) / n
         out["adam_after_rs_ms"] = sum(p["rs"][i].elapsed_time(p["adam"][i]) for i in range(n)) / n
         out["ag_exposed_ms"] = sum(p["adam"][i].elapsed_time(p["ag"][i]) for i in range(n)) / n
@@ -224,16 +228,28 @@ class ShardedTrainer:
         if self._nvls is not None:
             # reduce-scatter + sliced Adam + all-gather in ONE kernel over NVLink multicast (pda_exchange.cu), bracketed by
             # two cross-rank barriers on the compute stream (symmetric-memory signal pads)
-            h = self._nvls["hdl"]
+            nv = self._nvls
+            h, cur = nv["hdl"], nv["cur"]
             wacc = self._async_reduce(self._acc)
             m.adam_apply(stream, part=1)
             h.barrier(channel=0)                  # every rank's step kernel is done: the accumulators are complete
+            if cs is not None:
+                # the OTHER accumulator (step k-1's, fully read by every rank since that step's second barrier) is zeroed on a
+                # side stream under this NVLink-bound kernel; the next step accumulates into it
+                self._zs.wait_stream(cs)
+                with self._on(self._zs):
+                    nv["G"][1 - cur].zero_()
+                self._zero_pending = True
+            else:
+                nv["G"][1 - cur].zero_()
             lo, hi = self._own[0]
-            m.dp_exchange_adam(self._nvls["mcG"], self._nvls["mcW"], lo, hi, stream)
+            m.dp_exchange_adam(nv["mcG"][cur], nv["mcW"], lo, hi, stream)
             self._mark("rs")
             h.barrier(channel=1)                  # every replica written, every accumulator read
             self._mark("adam")
-            self._gi.zero_()
+            nv["cur"] = 1 - cur
+            self._gi = nv["G"][1 - cur]
+            m.set_item_grad_buffer(self._gi.data_ptr())
             self._mark("ag")
             wacc.wait()
             m.adam_apply(stream, part=8)
