@@ -97,7 +97,8 @@ class ShardedTrainer:
                     self._wi = torch.as_tensor(_DevArray(model.table_ptr("item_embedding"), (model.n_items, model.emb_dim),
                                                          "<f4"), device=dev)
                 self._side, self._zs, self._copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-                if scatter_ok and exchange in ("auto", "nvls"):
+                # auto: the multicast kernel pays off from 4 ranks on (2 GPUs: 2.89 vs 2.75 ms/step with NCCL; 8 GPUs: 2.61 vs 2.93)
+                if scatter_ok and (exchange == "nvls" or (exchange == "auto" and self.world >= 4)):
                     self._nvls = self._setup_nvls(dev)
                     if self._nvls is None and exchange == "nvls":
                         raise RuntimeError("exchange='nvls' requested but NVLink multicast (symmetric memory) is not available")

@@ -39,7 +39,13 @@ def _worker(rank, world, port, q, adam_mode, exchange):
         m.set_table("item_embedding", I)
         if adam_mode == "lazy":
             m.set_adam_mode("lazy")       # the trainer narrows it to lazy users + dense (all-reduced) items
-        tr = ShardedTrainer(m, world, rank, exchange=exchange)     # "auto": the fused NVLink-multicast kernel where available
+        try:
+            tr = ShardedTrainer(m, world, rank, exchange=exchange)     # "nvls": the fused NVLink-multicast kernel
+        except RuntimeError as e:
+            if exchange != "nvls":
+                raise
+            q.put((rank, "skip", str(e)))
+            return
         if rank == 0:
             print("exchange used:", tr.exchange, file=sys.stderr)
         stream = torch.cuda.current_stream().cuda_stream
@@ -62,7 +68,7 @@ def _worker(rank, world, port, q, adam_mode, exchange):
 
 
 @pytest.mark.timeout(600)
-@pytest.mark.parametrize("adam_mode,exchange", [("dense", "scatter"), ("lazy", "scatter"), ("lazy", "allreduce"), ("lazy", "auto")])
+@pytest.mark.parametrize("adam_mode,exchange", [("dense", "scatter"), ("lazy", "scatter"), ("lazy", "allreduce"), ("lazy", "nvls")])
 def test_two_gpus_equal_one_process_on_the_union_batch(c_oracle, adam_mode, exchange):
     if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
@@ -79,6 +85,8 @@ def test_two_gpus_equal_one_process_on_the_union_batch(c_oracle, adam_mode, exch
     for p in procs:
         p.join(60)
         assert p.exitcode == 0
+    if res[0][1] == "skip":
+        pytest.skip("NVLink multicast not available here: " + res[0][2])
     rng = np.random.default_rng(0)
     n_users, n_items, d, B = 4000, 900, 64, 256
     U = rng.normal(0, 0.3, (n_users, d)).astype(np.float32)
