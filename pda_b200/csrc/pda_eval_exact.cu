@@ -68,6 +68,15 @@ __global__ void __launch_bounds__(E_NT, 2) recommend_exact_kernel(EvalArgs a, in
     const int K = a.K, d = a.d;
     const int64_t Meff = a.M_dev ? (int64_t)*a.M_dev : a.M;    // device-sized launch (tensor path fallback rows)
     if (m0 >= Meff) return;
+    // few flagged rows: one CTA per (64-row block, item-range split), merged afterwards; many: one CTA per block
+    const bool split = a.n_split > 1;
+    if (split ? Meff > a.split_max_rows : (a.M_dev && Meff <= a.skip_rows_le)) return;
+    int64_t j_begin = 0, j_end = a.N;
+    if (split) {
+        const int64_t span = ((a.N + E_TN - 1) / E_TN + a.n_split - 1) / a.n_split * E_TN;
+        j_begin = (int64_t)blockIdx.y * span;
+        j_end = j_begin + span < a.N ? j_begin + span : a.N;
+    }
 
     for (int r = tid; r < E_TM; r += E_NT) {
         const int64_t m = m0 + r;
@@ -78,7 +87,7 @@ __global__ void __launch_bounds__(E_NT, 2) recommend_exact_kernel(EvalArgs a, in
     for (int e = tid; e < E_TM * Kp; e += E_NT) { tval[e] = -INFINITY; tid_[e] = 0x7fffffff; }
     __syncthreads();
 
-    for (int64_t j0 = 0; j0 < a.N; j0 += E_TN) {
+    for (int64_t j0 = j_begin; j0 < j_end; j0 += E_TN) {
         float acc[4][8];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
@@ -101,7 +110,7 @@ __global__ void __launch_bounds__(E_NT, 2) recommend_exact_kernel(EvalArgs a, in
                 const int idx = tid + E_NT * t, row = idx & (E_TN - 1), k4 = idx >> 7;
                 float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
                 const int64_t j = j0 + row;
-                if (j < a.N && kc + 4 * k4 < d) v = ldg_f4(a.I + j * d + kc + 4 * k4);
+                if (j < j_end && kc + 4 * k4 < d) v = ldg_f4(a.I + j * d + kc + 4 * k4);
                 Is[(4 * k4 + 0) * E_TN + row] = v.x; Is[(4 * k4 + 1) * E_TN + row] = v.y;
                 Is[(4 * k4 + 2) * E_TN + row] = v.z; Is[(4 * k4 + 3) * E_TN + row] = v.w;
             }
@@ -155,7 +164,7 @@ __global__ void __launch_bounds__(E_NT, 2) recommend_exact_kernel(EvalArgs a, in
 #pragma unroll
             for (int c = 0; c < E_TN / 32; ++c) {
                 const int64_t j = j0 + c * 32 + lane;
-                const bool valid = j < a.N;
+                const bool valid = j < j_end;
                 float y = -INFINITY;
                 if (valid) {
                     const float s = S[r * E_SLD + c * 32 + lane];
@@ -183,11 +192,60 @@ __global__ void __launch_bounds__(E_NT, 2) recommend_exact_kernel(EvalArgs a, in
         const int r = e / K, k = e - r * K;
         const int64_t m = m0 + r;
         if (m < Meff) {
-            const int64_t mo = a.out_rows ? (int64_t)a.out_rows[m] : m;
             const int idv = tid_[r * Kp + k];
+            if (split) {
+                a.part_ids[(m * a.n_split + blockIdx.y) * K + k] = idv;
+                a.part_val[(m * a.n_split + blockIdx.y) * K + k] = tval[r * Kp + k];
+                continue;
+            }
+            const int64_t mo = a.out_rows ? (int64_t)a.out_rows[m] : m;
             if (a.ids_out) a.ids_out[mo * K + k] = idv == 0x7fffffff ? -1 : idv;
             if (a.scores_out) a.scores_out[mo * K + k] = tval[r * Kp + k];
         }
+    }
+}
+
+// final top-K of a row from its n_split partial lists (each sorted, (score desc, id asc); unfilled slots = (-inf, 0x7fffffff)):
+// one CTA per row, bitonic sort of n_split * K 64-bit keys in shared memory
+__global__ void __launch_bounds__(256) recommend_merge_kernel(EvalArgs a) {
+    extern __shared__ unsigned long long mkeys[];
+    const int64_t Meff = a.M_dev ? (int64_t)*a.M_dev : a.M;
+    const int64_t m = blockIdx.x;
+    if (m >= Meff || Meff > a.split_max_rows) return;
+    const int K = a.K, n = a.n_split * K;
+    int n2 = 256;
+    while (n2 < n) n2 <<= 1;
+    for (int e = threadIdx.x; e < n2; e += 256) {
+        unsigned long long kv = 0ull;
+        if (e < n) {
+            const float y = a.part_val[m * n + e];
+            const uint32_t b = __float_as_uint(y);
+            const uint32_t key = (b & 0x80000000u) ? ~b : (b | 0x80000000u);             // order-preserving; -inf -> 0x007fffff > 0
+            kv = ((unsigned long long)key << 32) | (uint32_t)(0x7fffffff - a.part_ids[m * n + e]);
+        }
+        mkeys[e] = kv;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int idx = threadIdx.x; idx < n2; idx += 256) {
+                const int ixj = idx ^ j;
+                if (ixj > idx) {
+                    const unsigned long long x = mkeys[idx], y = mkeys[ixj];
+                    const bool desc = (idx & k) == 0;
+                    if (desc ? x < y : x > y) { mkeys[idx] = y; mkeys[ixj] = x; }
+                }
+            }
+            __syncthreads();
+        }
+    const int64_t mo = a.out_rows ? (int64_t)a.out_rows[m] : m;
+    for (int e = threadIdx.x; e < K; e += 256) {
+        const unsigned long long kv = mkeys[e];
+        const int idv = 0x7fffffff - (int32_t)(uint32_t)(kv & 0xffffffffu);
+        const uint32_t key = (uint32_t)(kv >> 32);
+        const float y = __uint_as_float((key & 0x80000000u) ? (key & 0x7fffffffu) : ~key);
+        if (a.ids_out) a.ids_out[mo * K + e] = idv == 0x7fffffff ? -1 : idv;
+        if (a.scores_out) a.scores_out[mo * K + e] = y;
     }
 }
 
@@ -196,13 +254,21 @@ int launch_recommend_exact(const EvalArgs& a, cudaStream_t st) {
     const int Kp = (a.K + 31) / 32 * 32;
     const size_t smem = sizeof(float) * (E_KC * E_TM + E_KC * E_TN + E_TM * E_SLD) + (size_t)E_TM * Kp * 8 +
                         E_TM * 4 * 4 + E_TM * 8 + E_TM * 4;
-    const int grid = (int)((a.M + E_TM - 1) / E_TM);
+    int64_t rows = a.M;
+    if (a.n_split > 1 && rows > a.split_max_rows) rows = a.split_max_rows;       // beyond that the plain form runs
+    const dim3 grid((unsigned)((rows + E_TM - 1) / E_TM), (unsigned)(a.n_split > 1 ? a.n_split : 1));
     if (a.mode == 1) {
         cudaFuncSetAttribute(recommend_exact_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         recommend_exact_kernel<1><<<grid, E_NT, smem, st>>>(a, Kp);
     } else {
         cudaFuncSetAttribute(recommend_exact_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         recommend_exact_kernel<0><<<grid, E_NT, smem, st>>>(a, Kp);
+    }
+    if (a.n_split > 1) {
+        int n2 = 256;
+        while (n2 < a.n_split * a.K) n2 <<= 1;
+        if (cudaFuncSetAttribute(recommend_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, n2 * 8) != cudaSuccess) return 2;
+        recommend_merge_kernel<<<(unsigned)rows, 256, (size_t)n2 * 8, st>>>(a);
     }
     return 0;
 }

@@ -1349,11 +1349,13 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->splits = (p->n_tiles + p->tiles_per_split - 1) / p->tiles_per_split;
     // candidate lists: one segment per (item split, column half); twice the expected total as head-room
     p->n_seg = p->splits * EPI_G;
-    const int cap_total = a.N <= 262144 ? 1024 : 4096;
+    // r2: a Douban model after 2 epochs delivers up to ~3000 candidates per row (train items knock out the top chunks, so tau
+    // is loose for heavy users); with 1024 / 512 half of the rows overflowed into the exact kernel (5.7 ms per eval)
+    const int cap_total = env_int("PDA_TC_CAP", a.N <= 262144 ? 8192 : 4096);
     p->seg_cap = ((2 * cap_total + p->n_seg - 1) / p->n_seg + 31) / 32 * 32;
     if (p->seg_cap < 64) p->seg_cap = 64;
     // compacted list a rescoring warp holds in shared memory: ~K * (1 + se) * 1.6 entries expected
-    p->rc = p->se <= 2 ? 512 : (p->se <= 6 ? 1024 : 2048);
+    p->rc = env_int("PDA_TC_RC", 2048);
     size_t o = 0;
     // item side first: these offsets depend on (N, d) only, so the item operands prepared for the first user block of a
     // call stay valid for the following blocks
@@ -1384,6 +1386,9 @@ size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* p) {
     p->o_ccount = o; o += al256((size_t)p->M_pad * 4);
     p->o_work = o; o += al256((size_t)p->M_pad * (p->rc / 32) * 4);
     p->o_nwork = o; o += 256;
+    // few-row fallback: partial top-K lists [FALLBACK_SPLIT_ROWS][FALLBACK_SPLITS][K]
+    p->o_partv = o; o += al256((size_t)FALLBACK_SPLIT_ROWS * FALLBACK_SPLITS * a.K * 4);
+    p->o_parti = o; o += al256((size_t)FALLBACK_SPLIT_ROWS * FALLBACK_SPLITS * a.K * 4);
     return o;
 }
 
@@ -1541,6 +1546,17 @@ int launch_recommend_tc(const EvalArgs& a, void* scratch, const TcPlan& p, bool 
     // rows without a certificate: the exact kernel, sized on the device (CTAs beyond ceil(n/64) exit at once)
     EvalArgs f = a;
     f.users = fusers; f.M_dev = nflag; f.out_rows = frows; f.dense_out = nullptr;
+    // few flagged rows (the usual case): item-range splits + merge, so the handful of rows does not crawl through all
+    // items inside ONE CTA (2.5 ms for a single row of 26 k items); many rows: one CTA per 64 rows as before
+    int ns = p.n_tiles / 4;
+    if (ns > FALLBACK_SPLITS) ns = FALLBACK_SPLITS;
+    if (ns > 1) {
+        EvalArgs g = f;
+        g.n_split = ns; g.split_max_rows = FALLBACK_SPLIT_ROWS;
+        g.part_val = (float*)(b + p.o_partv); g.part_ids = (int32_t*)(b + p.o_parti);
+        if (launch_recommend_exact(g, st)) return 31;
+        f.skip_rows_le = FALLBACK_SPLIT_ROWS;
+    }
     if (launch_recommend_exact(f, st)) return 30;
     return 0;
 }

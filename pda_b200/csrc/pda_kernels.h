@@ -70,13 +70,18 @@ struct EvalArgs {
     float* dense_out;                       // optional [M,N] transformed scores (unmasked)
     const int32_t* M_dev;                   // optional device-side row count (<= M): CTAs beyond it exit at once
     const int32_t* out_rows;                // optional [M] output row of each input row (scatter of fallback rows)
+    // fallback of FEW rows: the item range is split over blockIdx.y, partial top-K lists go to part_val / part_ids
+    // [row][split][K] and recommend_merge_kernel picks the final K.  Device-sized launches choose between the two forms:
+    // the split form runs only when *M_dev <= split_max_rows, the plain one only when *M_dev > skip_rows_le.
+    int n_split; int split_max_rows; int skip_rows_le;
+    float* part_val; int32_t* part_ids;
 };
 
 // plan + scratch layout of the tensor-core filter (pda_eval_tc.cu)
 struct TcPlan {
     int64_t M_pad, N_pad;
     int n_tiles, mr, ts, ordered, n_sel, se, cw, n_c, n_valid, splits, tiles_per_split, n_seg, seg_cap, rc;
-    size_t o_Ib, o_Ub, o_Ix, o_Ux, o_inorm, o_unorm, o_tnorm, o_tcolmax, o_targ, o_tcol2, o_torder, o_tpos, o_hotv, o_hoti, o_cmax, o_tau, o_cnt, o_cand, o_flag, o_frows, o_fusers, o_nflag, o_clist, o_ckeys, o_ccount, o_work, o_nwork;
+    size_t o_Ib, o_Ub, o_Ix, o_Ux, o_inorm, o_unorm, o_tnorm, o_tcolmax, o_targ, o_tcol2, o_torder, o_tpos, o_hotv, o_hoti, o_cmax, o_tau, o_cnt, o_cand, o_flag, o_frows, o_fusers, o_nflag, o_clist, o_ckeys, o_ccount, o_work, o_nwork, o_partv, o_parti;
 };
 
 void launch_xavier_init(float* W, int64_t rows, int cols, uint32_t seed, uint32_t table_id, cudaStream_t st);
@@ -101,6 +106,7 @@ void launch_f32_to_i32(const float* src, int32_t* dst, int64_t n, int32_t max_va
 void launch_temp_item_bias(const float* ub, const float* ib, int64_t n_items, int temp_num, int32_t first_user,
                            float* out, cudaStream_t st);
 int launch_recommend_exact(const EvalArgs& a, cudaStream_t st);
+constexpr int FALLBACK_SPLIT_ROWS = 1024, FALLBACK_SPLITS = 64;   // few-row fallback of the tensor path (pda_eval_exact.cu)
 bool tc_supported(const EvalArgs& a);
 size_t tc_scratch_bytes(const EvalArgs& a, TcPlan* plan);
 // ev: optional 4 events recorded around the sampled sweep (ev[0], ev[1]) and the full sweep (ev[2], ev[3])
