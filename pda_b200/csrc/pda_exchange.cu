@@ -30,6 +30,16 @@ __device__ __forceinline__ void multimem_st(float* mc, const float4& v) {
     asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+__device__ __forceinline__ void multimem_st_weak(float* mc, const float4& v) {
+    asm volatile("multimem.st.weak.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 multimem_ld_reduce_add_weak(const float* mc) {
+    float4 v;
+    asm volatile("multimem.ld_reduce.weak.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(mc) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void adam_elem_x(float& w, float& m, float& v, float g, float lr_t) {
     const float omb1 = fsub(1.0f, 0.9f), omb2 = fsub(1.0f, 0.999f);
     m = fadd(fmul(m, 0.9f), fmul(g, omb1));
@@ -53,7 +63,8 @@ __global__ void __launch_bounds__(256) dp_exchange_adam_kernel(const float* __re
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const int64_t e = base + (int64_t)u * blockDim.x;
-            if (e < n4) g[u] = (dbg & 1) ? multimem_ld_reduce_add(mcG + 4 * e) : reinterpret_cast<const float4*>(Gl)[e];
+            if (e < n4) g[u] = (dbg & 1) ? ((dbg & 8) ? multimem_ld_reduce_add_weak(mcG + 4 * e) : multimem_ld_reduce_add(mcG + 4 * e))
+                                         : reinterpret_cast<const float4*>(Gl)[e];
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -66,7 +77,8 @@ __global__ void __launch_bounds__(256) dp_exchange_adam_kernel(const float* __re
             adam_elem_x(w.w, m.w, v.w, g[u].w, lr_t);
             reinterpret_cast<float4*>(M)[e] = m;
             reinterpret_cast<float4*>(V)[e] = v;
-            if (dbg & 2) multimem_st(mcW + 4 * e, w);          // every replica, this rank's included
+            if (dbg & 4) multimem_st_weak(mcW + 4 * e, w);
+            else if (dbg & 2) multimem_st(mcW + 4 * e, w);     // every replica, this rank's included
             else reinterpret_cast<float4*>(W)[e] = w;
         }
     }

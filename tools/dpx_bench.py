@@ -25,6 +25,12 @@ for blocks in ((148, 296, 592) if world > 2 else (32, 74, 148, 296, 592, 1184)):
         variants.append(dict(PDA_DPX_BLOCKS=blocks, PDA_DPX_UNROLL=unroll, PDA_DPX_DBG=3))
 for dbg in (0, 1, 2):
     variants.append(dict(PDA_DPX_BLOCKS=592, PDA_DPX_UNROLL=4, PDA_DPX_DBG=dbg))
+for dbg in (3 | 4, 3 | 8, 3 | 4 | 8):      # weak multimem stores / loads
+    for unroll in (2, 8):
+        variants.append(dict(PDA_DPX_BLOCKS=296, PDA_DPX_UNROLL=unroll, PDA_DPX_DBG=dbg))
+variants.append(dict(PDA_DPX_BLOCKS=296, PDA_DPX_UNROLL=8, PDA_DPX_DBG=3))
+variants.append(dict(PDA_DPX_BLOCKS=74, PDA_DPX_UNROLL=8, PDA_DPX_DBG=3))
+variants.append(dict(PDA_DPX_BLOCKS=1184, PDA_DPX_UNROLL=1, PDA_DPX_DBG=3))
 for v in variants:
     os.environ.update({k: str(x) for k, x in v.items()})
     ts = []
