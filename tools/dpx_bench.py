@@ -38,7 +38,7 @@ for v in variants:
         h.barrier(channel=0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        m.dp_exchange_adam(tr._nvls["mcG"], tr._nvls["mcW"], lo, hi, 0)
+        m.dp_exchange_adam(tr._nvls["mcG"][0], tr._nvls["mcW"], lo, hi, 0)
         e1.record()
         h.barrier(channel=1)
         torch.cuda.synchronize()
