@@ -133,6 +133,14 @@ int main(int argc, char** argv) {
         hu[i] = (int)((i * 7919ull * 1013ull + xr() % 9) % nU);
         double r = (xr() % 1000000) / 1e6; hp[i] = (int)(exp(r * log((double)nI + 1)) - 1) % nI; hn[i] = xr() % nI;
     }
+    if (argc > 2 && atoi(argv[2]) == 1) {      // batch sorted by pos item (the order of triples inside a batch is free)
+        struct T { int u, p, n; };
+        T* t = (T*)malloc(B * sizeof(T));
+        for (int64_t i = 0; i < B; ++i) t[i] = {hu[i], hp[i], hn[i]};
+        qsort(t, B, sizeof(T), [](const void* a, const void* b) { return ((const T*)a)->p - ((const T*)b)->p; });
+        for (int64_t i = 0; i < B; ++i) { hu[i] = t[i].u; hp[i] = t[i].p; hn[i] = t[i].n; }
+        printf("batch sorted by pos item\n");
+    }
     cudaMalloc(&iu, B * 4); cudaMalloc(&ip, B * 4); cudaMalloc(&in, B * 4);
     cudaMemcpy(iu, hu, B * 4, cudaMemcpyHostToDevice); cudaMemcpy(ip, hp, B * 4, cudaMemcpyHostToDevice); cudaMemcpy(in, hn, B * 4, cudaMemcpyHostToDevice);
     const double gb = B * (40.0 * 128 + 20) / 1e9;
