@@ -207,6 +207,11 @@ int pda_adopt_item_buffers(pda_model* m, float* W_ext, float* G_ext);
 /* switch the accumulator to another caller-owned ZERO-filled buffer (double buffering; after pda_adopt_item_buffers) */
 int pda_set_item_grad_buffer(pda_model* m, float* G_ext);
 int pda_dp_exchange_adam(pda_model* m, const float* mcG, float* mcW, int64_t row_lo, int64_t row_hi, void* stream);
+/* the same kernel over UNICAST peer pointers (2 ranks: same wire volume, nothing for the switch to reduce): peer_G[r] /
+ * peer_W[r] = rank r's accumulator / table as mapped in this process, r = 0..world-1 (<= 8), self included; the partial
+ * gradients are added in rank order */
+int pda_dp_exchange_adam_p2p(pda_model* m, const float* const* peer_G, float* const* peer_W, int32_t world, int32_t self,
+                             int64_t row_lo, int64_t row_hi, void* stream);
 int pda_stage_batch_host(pda_model* m, const int32_t* users, const int32_t* pos, const int32_t* neg,
                          const float* pos_pop, const float* neg_pop, int64_t B, void* stream);
 /* pda_stage_batch_host without blocking: the copies and the device-side id check (ids inside their tables, users

@@ -792,6 +792,24 @@ int pda_dp_exchange_adam(pda_model* m, const float* mcG, float* mcW, int64_t row
     return PDA_OK;
 }
 
+// the same over unicast peer pointers: peer_G[r] / peer_W[r] = rank r's accumulator / table as mapped in THIS process
+// (symmetric memory), r = 0..world-1, self included
+int pda_dp_exchange_adam_p2p(pda_model* m, const float* const* peer_G, float* const* peer_W, int32_t world, int32_t self,
+                             int64_t row_lo, int64_t row_hi, void* stream) {
+    if (!m || !peer_G || !peer_W || world < 1 || world > 8 || self < 0 || self >= world) return fail(PDA_ERR_ARG, "bad argument");
+    if (row_lo < 0 || row_hi > m->nI || row_lo > row_hi) return fail(PDA_ERR_ARG, "row range outside the item table");
+    if (m->adam_lazy[1]) return fail(PDA_ERR_STATE, "the item table is kept lazily: there is no dense sweep to run on it");
+    if (peer_W[self] != m->W[1]) return fail(PDA_ERR_STATE, "peer_W[self] is not the model's (adopted) item table");
+    if (row_lo == row_hi) return PDA_OK;
+    CK(cudaSetDevice(m->cfg.device));
+    const size_t off = (size_t)row_lo * m->d;
+    { ProfScope ps(m, PDA_PROF_ADAM, (cudaStream_t)stream);
+      launch_dp_exchange_adam_p2p(peer_G, peer_W, world, self, (int64_t)off, m->Mo[1] + off, m->Vo[1] + off, (row_hi - row_lo) * m->d / 4,
+                                  m->pw, m->cfg.lr, (cudaStream_t)stream); }
+    CK(cudaGetLastError());
+    return PDA_OK;
+}
+
 int pda_adam_apply_part(pda_model* m, int part, void* stream) {
     if (!m || (part != 1 && part != 2 && part != 3 && part != 8)) return fail(PDA_ERR_ARG, "bad argument");
     CK(cudaSetDevice(m->cfg.device));

@@ -97,6 +97,8 @@ void launch_dp_exchange_adam(const float* mcG, float* mcW, const float* Gl, floa
 size_t segsum_temp_bytes(int64_t n);
 int launch_segment_sum(const int32_t* a, const int32_t* b, int64_t B, const float* rows, int d, float* G, int32_t* work, void* temp,
                        size_t temp_bytes, int key_bits, cudaStream_t st);   // pda_segsum.cu
+void launch_dp_exchange_adam_p2p(const float* const* G, float* const* W, int world, int self, int64_t off, float* M, float* V,
+                                 int64_t n4, const float* pw, float lr, cudaStream_t st);
 int launch_adam_lazy_rows(const LazyArgs& a, int phase, cudaStream_t st);
 void launch_adam_lazy_flush(const LazyArgs& a, int tbl, int64_t n_rows, cudaStream_t st);
 void launch_batch_check(const int32_t* users, const int32_t* pos, const int32_t* neg, int64_t B, int32_t n_users,

@@ -300,6 +300,14 @@ class PDAModel:
         check(self.lib.pda_dp_exchange_adam(self._h, ptr(int(mc_G)), ptr(int(mc_W)), int(row_lo), int(row_hi),
                                             ptr(stream) if stream else None))
 
+    def dp_exchange_adam_p2p(self, peer_G, peer_W, self_rank, row_lo, row_hi, stream=0):
+        """the fused exchange over unicast peer pointers (lists of device addresses, one per rank, self included)"""
+        w = len(peer_G)
+        g = (C.c_void_p * w)(*[int(x) for x in peer_G])
+        ww = (C.c_void_p * w)(*[int(x) for x in peer_W])
+        check(self.lib.pda_dp_exchange_adam_p2p(self._h, C.cast(g, C.c_void_p), C.cast(ww, C.c_void_p), w, int(self_rank), int(row_lo),
+                                                int(row_hi), ptr(stream) if stream else None))
+
     def stage_batch_async(self, users, pos_items, neg_items, pos_pop=None, neg_pop=None, copy_stream=0):
         """enqueue the host->device copies (+ the id / distinct-users check) of a PINNED host batch on `copy_stream` and
         return; staged_batch_wait() completes it.  The arrays must stay alive until then."""

@@ -97,17 +97,21 @@ class ShardedTrainer:
                     self._wi = torch.as_tensor(_DevArray(model.table_ptr("item_embedding"), (model.n_items, model.emb_dim),
                                                          "<f4"), device=dev)
                 self._side, self._zs, self._copy = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-                # auto: the multicast kernel pays off from 4 ranks on (2 GPUs: 2.89 vs 2.75 ms/step with NCCL; 8 GPUs: 2.61 vs 2.93)
-                if scatter_ok and (exchange == "nvls" or (exchange == "auto" and self.world >= 4)):
-                    self._nvls = self._setup_nvls(dev)
-                    if self._nvls is None and exchange == "nvls":
-                        raise RuntimeError("exchange='nvls' requested but NVLink multicast (symmetric memory) is not available")
+                # auto: symmetric memory + the fused exchange kernel -- over the multicast mapping from 4 ranks on (in-switch
+                # reduction: 8 GPUs 2.49 vs 2.93 ms/step with NCCL), over unicast peer pointers below ("p2p")
+                if scatter_ok and exchange in ("nvls", "p2p", "auto"):
+                    unicast = exchange == "p2p" or (exchange == "auto" and self.world < 4)
+                    self._nvls = self._setup_nvls(dev, need_multicast=not unicast)
+                    if self._nvls is not None:
+                        self._nvls["unicast"] = unicast
+                    if self._nvls is None and exchange in ("nvls", "p2p"):
+                        raise RuntimeError("exchange=%r requested but symmetric memory / NVLink multicast is not available" % exchange)
             if self._nvls is not None:
                 rows = model.n_items // self.world
                 self.nch = 1
                 self._own = [(self.rank * rows, (self.rank + 1) * rows)]
                 self._chunk = [(0, model.n_items)]
-                self.exchange = "nvls"
+                self.exchange = "p2p" if self._nvls["unicast"] else "nvls"
             elif self._wi is not None:
                 self.exchange = "scatter"
                 # The exchange runs in `nch` row chunks; inside chunk c (rows [c R, (c+1) R), R = n_items / nch) rank r
@@ -132,7 +136,7 @@ class ShardedTrainer:
                         self._pg_ag = dist.new_group(backend="nccl")
         self._prof = None
 
-    def _setup_nvls(self, dev):
+    def _setup_nvls(self, dev, need_multicast=True):
         """item table + item-gradient accumulator into symmetric memory with a multicast mapping (torch plumbing); None when
         the platform has no NVLink multicast.  Collective: every rank calls it."""
         import torch
@@ -149,9 +153,11 @@ class ShardedTrainer:
             buf = symm.empty(3 * n, dtype=torch.float32, device=dev)      # [W | G0 | G1]: the accumulator is double-buffered
             hdl = symm.rendezvous(buf, dist.group.WORLD)
             mc = int(hdl.multicast_ptr)
-            if mc == 0:
+            if mc == 0 and need_multicast:
                 ok = 0
-            st = dict(buf=buf, hdl=hdl, mcW=mc, mcG=[mc + 4 * n, mc + 8 * n], cur=0)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            st = dict(buf=buf, hdl=hdl, mcW=mc, mcG=[mc + 4 * n, mc + 8 * n], cur=0, peerW=ptrs,
+                      peerG=[[x + 4 * n for x in ptrs], [x + 8 * n for x in ptrs]])
         except Exception as e:      # no symmetric memory on this platform / torch build
             import sys
             print("pda_b200: NVLink multicast exchange unavailable (%r); using the NCCL exchange" % (e,), file=sys.stderr)
@@ -205,7 +211,7 @@ class ShardedTrainer:
         p = self._prof
         n = min(len(p["fwd"]), len(p["rs"]), len(p["adam"]), len(p["ag"]))
         out = {"steps": n, "exchange": self.exchange, "chunks": self.nch, "two_communicators": getattr(self, "_pg_ag", None) is not None}
-        if self.exchange == "nvls":
+        if self.exchange in ("nvls", "p2p"):
             out["phases"] = ("rs_exposed = barrier + fused multimem kernel (the other accumulator is zeroed under it), "
                              "adam_after_rs = second barrier, ag_exposed = 0 (nothing left on the critical path)")
         out["rs_exposed_ms"] = sum(p["fwd"][i].elapsed_time(p["rs"][i]) for i in range(n)) / n
@@ -244,7 +250,10 @@ class ShardedTrainer:
             else:
                 nv["G"][1 - cur].zero_()
             lo, hi = self._own[0]
-            m.dp_exchange_adam(nv["mcG"][cur], nv["mcW"], lo, hi, stream)
+            if nv["unicast"]:
+                m.dp_exchange_adam_p2p(nv["peerG"][cur], nv["peerW"], self.rank, lo, hi, stream)
+            else:
+                m.dp_exchange_adam(nv["mcG"][cur], nv["mcW"], lo, hi, stream)
             self._mark("rs")
             h.barrier(channel=1)                  # every replica written, every accumulator read
             self._mark("adam")
