@@ -99,10 +99,20 @@ __device__ __forceinline__ void st_sys_f4(float* p, const float4& v) {
     asm volatile("st.global.relaxed.sys.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_weak_f4(float* p, const float4& v) {
+    asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// mode bit 0: ld.global.cg instead of ld.relaxed.sys; bit 1: plain (weak) stores instead of st.relaxed.sys
 template <int U>
 __global__ void __launch_bounds__(256) dp_exchange_adam_p2p_kernel(PeerPtrs pp, int world, int self, float* __restrict__ M,
                                                                    float* __restrict__ V, int64_t n4, const float* __restrict__ pw,
-                                                                   float lr) {
+                                                                   float lr, int mode) {
     const float lr_t = fdiv(fmul(lr, fsqrt(fsub(1.0f, pw[1]))), fsub(1.0f, pw[0]));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n4; base += stride) {
@@ -112,9 +122,9 @@ __global__ void __launch_bounds__(256) dp_exchange_adam_p2p_kernel(PeerPtrs pp, 
             const int64_t e = base + (int64_t)u * blockDim.x;
             g[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (e < n4) {
-                g[u] = ld_sys_f4(pp.G[0] + 4 * e);                   // 0 + g0 == g0: start from rank 0's partial
+                g[u] = (mode & 1) ? ld_cg_f4(pp.G[0] + 4 * e) : ld_sys_f4(pp.G[0] + 4 * e);   // 0 + g0 == g0: start from rank 0's partial
                 for (int r = 1; r < world; ++r) {
-                    const float4 t = ld_sys_f4(pp.G[r] + 4 * e);
+                    const float4 t = (mode & 1) ? ld_cg_f4(pp.G[r] + 4 * e) : ld_sys_f4(pp.G[r] + 4 * e);
                     g[u].x = fadd(g[u].x, t.x); g[u].y = fadd(g[u].y, t.y); g[u].z = fadd(g[u].z, t.z); g[u].w = fadd(g[u].w, t.w);
                 }
             }
@@ -130,7 +140,7 @@ __global__ void __launch_bounds__(256) dp_exchange_adam_p2p_kernel(PeerPtrs pp, 
             adam_elem_x(w.w, m.w, v.w, g[u].w, lr_t);
             reinterpret_cast<float4*>(M)[e] = m;
             reinterpret_cast<float4*>(V)[e] = v;
-            for (int r = 0; r < world; ++r) st_sys_f4(pp.W[r] + 4 * e, w);
+            for (int r = 0; r < world; ++r) { if (mode & 2) st_weak_f4(pp.W[r] + 4 * e, w); else st_sys_f4(pp.W[r] + 4 * e, w); }
         }
     }
 }
@@ -157,14 +167,15 @@ void launch_dp_exchange_adam_p2p(const float* const* G, float* const* W, int wor
                                  int64_t n4, const float* pw, float lr, cudaStream_t st) {
     PeerPtrs pp;
     for (int r = 0; r < 8; ++r) { pp.G[r] = r < world ? G[r] + off : nullptr; pp.W[r] = r < world ? W[r] + off : nullptr; }
-    const int U = env_i("PDA_DPX_UNROLL", 2);
+    const int U = env_i("PDA_DPX_UNROLL", 2), mode = env_i("PDA_DPX_P2P_MODE", 0);
     int64_t blocks = (n4 + 256 * U - 1) / (256 * U);
     const int cap = env_i("PDA_DPX_BLOCKS", 148 * 4);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (U == 1) dp_exchange_adam_p2p_kernel<1><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr);
-    else if (U == 4) dp_exchange_adam_p2p_kernel<4><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr);
-    else dp_exchange_adam_p2p_kernel<2><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr);
+    if (U == 1) dp_exchange_adam_p2p_kernel<1><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode);
+    else if (U == 4) dp_exchange_adam_p2p_kernel<4><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode);
+    else if (U == 8) dp_exchange_adam_p2p_kernel<8><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode);
+    else dp_exchange_adam_p2p_kernel<2><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode);
 }
 
 }  // namespace pda

@@ -16,7 +16,8 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 n_items, d = 1_000_000, 128
 m = pda_b200.PDAModel(4096, n_items, d, train="s_condition", batch_size=1024, device=local, seed=2021)
-tr = ShardedTrainer(m, world, rank, exchange="nvls")
+P2P = os.environ.get("DPX_P2P", "0") == "1"
+tr = ShardedTrainer(m, world, rank, exchange="p2p" if P2P else "nvls")
 h = tr._nvls["hdl"]
 lo, hi = tr._own[0]
 variants = []
@@ -31,6 +32,8 @@ for dbg in (3 | 4, 3 | 8, 3 | 4 | 8):      # weak multimem stores / loads
 variants.append(dict(PDA_DPX_BLOCKS=296, PDA_DPX_UNROLL=8, PDA_DPX_DBG=3))
 variants.append(dict(PDA_DPX_BLOCKS=74, PDA_DPX_UNROLL=8, PDA_DPX_DBG=3))
 variants.append(dict(PDA_DPX_BLOCKS=1184, PDA_DPX_UNROLL=1, PDA_DPX_DBG=3))
+if P2P:
+    variants = [dict(PDA_DPX_BLOCKS=b, PDA_DPX_UNROLL=u, PDA_DPX_P2P_MODE=md) for md in (0, 1, 2, 3) for b in (148, 592, 1184) for u in (2, 4, 8)]
 for v in variants:
     os.environ.update({k: str(x) for k, x in v.items()})
     ts = []
@@ -38,7 +41,10 @@ for v in variants:
         h.barrier(channel=0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        m.dp_exchange_adam(tr._nvls["mcG"][0], tr._nvls["mcW"], lo, hi, 0)
+        if P2P:
+            m.dp_exchange_adam_p2p(tr._nvls["peerG"][0], tr._nvls["peerW"], rank, lo, hi, 0)
+        else:
+            m.dp_exchange_adam(tr._nvls["mcG"][0], tr._nvls["mcW"], lo, hi, 0)
         e1.record()
         h.barrier(channel=1)
         torch.cuda.synchronize()
