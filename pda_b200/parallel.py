@@ -82,7 +82,7 @@ class ShardedTrainer:
                 self._reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM)
                 if hasattr(model, "adam_dense_rows_ext"):     # split optimizer available: asynchronous work handles
                     self._async_reduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
-            scatter_ok = exchange in ("scatter", "auto", "nvls") and self._async_reduce is not None and model.n_items % self.world == 0
+            scatter_ok = exchange in ("scatter", "auto", "nvls", "p2p") and self._async_reduce is not None and model.n_items % self.world == 0
             if hasattr(model, "exchange_tensors"):     # host stand-ins (tests) hand their buffers over directly
                 ex = model.exchange_tensors()
                 self._gi, self._acc = ex[0], ex[1]

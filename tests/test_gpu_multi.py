@@ -48,6 +48,7 @@ def _worker(rank, world, port, q, adam_mode, exchange):
             return
         if rank == 0:
             print("exchange used:", tr.exchange, file=sys.stderr)
+        assert exchange == "auto" or tr.exchange == exchange, (exchange, tr.exchange)
         stream = torch.cuda.current_stream().cuda_stream
         losses = []
         for step in range(6):
