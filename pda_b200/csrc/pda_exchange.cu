@@ -169,7 +169,8 @@ void launch_dp_exchange_adam_p2p(const float* const* G, float* const* W, int wor
     for (int r = 0; r < 8; ++r) { pp.G[r] = r < world ? G[r] + off : nullptr; pp.W[r] = r < world ? W[r] + off : nullptr; }
     const int U = env_i("PDA_DPX_UNROLL", 2), mode = env_i("PDA_DPX_P2P_MODE", 0);
     int64_t blocks = (n4 + 256 * U - 1) / (256 * U);
-    const int cap = env_i("PDA_DPX_BLOCKS", 148 * 4);
+    // measured at 2 GPUs (256 MB slice): 148 CTAs 1.63 ms, 592 -> 0.83-0.88, 1184 x unroll 2 -> 0.785; ld/st flavours equal
+    const int cap = env_i("PDA_DPX_BLOCKS", 148 * 8);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     if (U == 1) dp_exchange_adam_p2p_kernel<1><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode);
