@@ -71,6 +71,10 @@ def test_douban_pd_training_and_pda_eval_match_oracle(douban, c_oracle):
     users = np.asarray(d.valid_user_list.keys(), dtype=np.int32)
     for rec_type, p in (("main_branch", None), ("condition", last), ("condition", lin)):
         ids = m.do_recommendation(users, None, rec_type, pos_pop=p, K=50)
+        st = m.tc_last_stats()
+        # the filter carries the load on a model that has started to fit (heavy users' train items loosen tau: the candidate
+        # capacity must hold them) -- at most a handful of rows may need the exact kernel
+        assert st["rows_exact_fallback"] <= 0.01 * len(users), (rec_type, st)
         got = m.metrics_sum(ids, users, d.valid_indptr, d.valid_items, [20, 50])
         rid, _ = c_oracle.recommend(ref.U, ref.I, users, rec_type, 50, d.train_indptr, d.train_items, pop=p)
         want = c_oracle.metrics_sum(rid, users, d.valid_indptr, d.valid_items, [20, 50])
