@@ -408,7 +408,8 @@ __global__ void __launch_bounds__(1024) tc_tile_select_kernel(const float* __res
 struct SweepArgs {
     int64_t M, N;              // real rows / items
     int64_t M_pad;             // rows of the bf16 user copy (multiple of MR * 128)
-    int d, kx;                 // kx = 1: the 16-column extra K block is present
+    int d, kx;                 // kx = 1: a column term x_j (pop / bias) enters the accumulators
+    const float* xcol; int xinit;   // xinit = 1: x_j is written into the accumulators before the MMAs (no extra K block)
     int n_tiles;               // item tiles of 128
     int tiles_per_split;       // each CTA of blockIdx.y sweeps [y * tiles_per_split, ...)
     int se;                    // pass A samples n_sel = ceil(n_tiles / se) tiles:
@@ -484,7 +485,10 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float thr, i
 
 }  // namespace tc
 
-// KBLK = d / 64 K blocks; KXT = 1: the 16-column extra K block is present; MR user tiles per CTA;
+// KBLK = d / 64 K blocks; MR user tiles per CTA; how the column term x_j (pop / bias) enters the accumulator v_j:
+//   KXT = 1: a 16-column extra K block, user side (1,1,1,0..), item side the three bf16 pieces of x_j (one more MMA of 9);
+//   KXT = 2: the epilogue warps WRITE x_j (fp32, exact) into the accumulator with tcgen05.st right after they have read the
+//            previous tile out of it, and every MMA accumulates -- K stays d: 8 MMAs per tile instead of 9 at d = 128;
 // TS = 1: the user tiles live in TENSOR memory (tcgen05.mma with the A operand from TMEM): the tensor core then reads
 // only the B tile from shared memory per instruction (64 B/cycle instead of the 128 B/cycle of the shared-memory form
 // at N = 128, which is the whole shared-memory bandwidth of the SM and capped the tensor pipe at ~85 %), and all of the
@@ -496,15 +500,17 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                                                               const __grid_constant__ CUtensorMap tmBx, SweepArgs a,
                                                               int n_stages) {
     using namespace tc;
+    constexpr bool XB = KXT == 1, XI = KXT == 2;
+    static_assert(!(XI && TS), "accumulator pre-initialisation is implemented for the shared-memory operand form");
     constexpr int ACC = TS ? 2 : MR;                             // TS: ring of two accumulators; else accumulator mr <-> user tile mr
-    constexpr int A_COLS = (KBLK * KB + (KXT ? KX : 0)) / 2;     // TS: 32-bit TMEM columns of one user tile
+    constexpr int A_COLS = (KBLK * KB + (XB ? KX : 0)) / 2;      // TS: 32-bit TMEM columns of one user tile
     static_assert(MR >= 1 && MR <= MR_MAX && ACC * TN + (TS ? MR * A_COLS : 0) <= TMEM_COLS, "tensor memory budget");
     extern __shared__ unsigned char smem_raw[];
     // 1024 B alignment for the 128B-swizzle atoms
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    constexpr uint32_t a1_bytes = A_KB_BYTES * KBLK + (KXT ? A_KX_BYTES : 0u);     // one user tile: K blocks + extra block
+    constexpr uint32_t a1_bytes = A_KB_BYTES * KBLK + (XB ? A_KX_BYTES : 0u);      // one user tile: K blocks + extra block
     constexpr uint32_t a_bytes = TS ? 0u : a1_bytes * MR;                          // MR user tiles stay resident for the whole sweep
-    constexpr uint32_t b_bytes = B_KB_BYTES * KBLK + (KXT ? B_KX_BYTES : 0u);      // one B stage
+    constexpr uint32_t b_bytes = B_KB_BYTES * KBLK + (XB ? B_KX_BYTES : 0u);       // one B stage
     unsigned char* sA = smem;
     unsigned char* sB = smem + a_bytes;
     unsigned char* tail_p = sB + (size_t)n_stages * b_bytes;
@@ -552,7 +558,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                     const int r0 = (m_blk * MR + mr) * TM;
 #pragma unroll
                     for (int kb = 0; kb < KBLK; ++kb) tma_load_2d(at + (uint32_t)kb * A_KB_BYTES, &tmA, bar_afull, kb * KB, r0);
-                    if (KXT) tma_load_2d(at + (uint32_t)KBLK * A_KB_BYTES, &tmAx, bar_afull, 0, r0);
+                    if (XB) tma_load_2d(at + (uint32_t)KBLK * A_KB_BYTES, &tmAx, bar_afull, 0, r0);
                 }
             }
             __syncwarp();
@@ -568,7 +574,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                     const uint32_t bt = smem_u32(sB) + (uint32_t)s * b_bytes;
 #pragma unroll
                     for (int kb = 0; kb < KBLK; ++kb) tma_load_2d(bt + (uint32_t)kb * B_KB_BYTES, &tmB, bar_full + 8 * s, kb * KB, t * TN);
-                    if (KXT) tma_load_2d(bt + (uint32_t)KBLK * B_KB_BYTES, &tmBx, bar_full + 8 * s, 0, t * TN);
+                    if (XB) tma_load_2d(bt + (uint32_t)KBLK * B_KB_BYTES, &tmBx, bar_full + 8 * s, 0, t * TN);
                 }
                 __syncwarp();
                 if (++s == n_stages) { s = 0; ph ^= 1; }
@@ -590,7 +596,8 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                     const int sub = i * MR + mr;
                     const int acc = TS ? (sub & 1) : mr;
                     const uint32_t aph = TS ? (uint32_t)(sub >> 1) & 1u : (uint32_t)i & 1u;
-                    mbar_wait(bar_tempty + 8 * acc, aph ^ 1u);
+                    // XI: the epilogue arrives once more per accumulator before the first tile (after writing x_j into it)
+                    mbar_wait(bar_tempty + 8 * acc, XI ? aph : aph ^ 1u);
                     fence_after();
                     if (elect_one()) {
                         const uint32_t d_tmem = tmem_base + (uint32_t)acc * TN;
@@ -602,7 +609,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                                 for (int k = 0; k < KB / 16; ++k)
                                     umma_bf16_ts(d_tmem, at + (uint32_t)(kb * (KB / 2) + k * 8),
                                                  make_desc_hl(DESC_HI_SW128, b_lo + kb * (B_KB_BYTES >> 4) + k * 2), IDESC, (kb | k) ? 1u : 0u);
-                            if (KXT)
+                            if (XB)
                                 umma_bf16_ts(d_tmem, at + (uint32_t)(KBLK * (KB / 2)),
                                              make_desc_hl(DESC_HI_SW32, b_lo + KBLK * (B_KB_BYTES >> 4)), IDESC, 1u);
                         } else {
@@ -612,8 +619,9 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
 #pragma unroll
                                 for (int k = 0; k < KB / 16; ++k)    // UMMA K = 16 bf16 = 32 B inside the 128 B swizzle row
                                     umma_bf16(d_tmem, make_desc_hl(DESC_HI_SW128, am + kb * (A_KB_BYTES >> 4) + k * 2),
-                                              make_desc_hl(DESC_HI_SW128, b_lo + kb * (B_KB_BYTES >> 4) + k * 2), IDESC, (kb | k) ? 1u : 0u);
-                            if (KXT)                                 // + x_j: (1, 1, 1, 0...) . (x_hi, x_mid, x_lo, 0...)
+                                              make_desc_hl(DESC_HI_SW128, b_lo + kb * (B_KB_BYTES >> 4) + k * 2), IDESC,
+                                              (XI || (kb | k)) ? 1u : 0u);
+                            if (XB)                                  // + x_j: (1, 1, 1, 0...) . (x_hi, x_mid, x_lo, 0...)
                                 umma_bf16(d_tmem, make_desc_hl(DESC_HI_SW32, am + KBLK * (A_KB_BYTES >> 4)),
                                           make_desc_hl(DESC_HI_SW32, b_lo + KBLK * (B_KB_BYTES >> 4)), IDESC, 1u);
                         }
@@ -659,7 +667,7 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                     }
                     tmem_st32(at + (uint32_t)(kb * 32), w);
                 }
-                if (KXT) {
+                if (XB) {
                     const uint4* sx = reinterpret_cast<const uint4*>(a.Ux + row[mr] * (int64_t)KX);
                     const uint4 v0 = __ldg(sx), v1 = __ldg(sx + 1);
                     w[0] = v0.x; w[1] = v0.y; w[2] = v0.z; w[3] = v0.w; w[4] = v1.x; w[5] = v1.y; w[6] = v1.z; w[7] = v1.w;
@@ -672,8 +680,41 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
             if (lane == 0) mbar_arrive(bar_afull);
         }
         const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(h * EPI_COLS);
+        // XI: this thread's 64 columns of accumulator `acc` <- x_j of tile `tile` (0 beyond N); every lane writes its own row
+        const bool x_al = (reinterpret_cast<uintptr_t>(a.xcol) & 15u) == 0;
+        auto init_acc = [&](int acc, int tile) {
+            const int64_t jb = (int64_t)tile * TN + h * EPI_COLS;
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                uint32_t w[32];
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const int64_t j = jb + half * 32 + c4 * 4;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (x_al && j + 3 < a.N) x = __ldg(reinterpret_cast<const float4*>(a.xcol + j));
+                    else {
+                        if (j < a.N) x.x = __ldg(a.xcol + j);
+                        if (j + 1 < a.N) x.y = __ldg(a.xcol + j + 1);
+                        if (j + 2 < a.N) x.z = __ldg(a.xcol + j + 2);
+                        if (j + 3 < a.N) x.w = __ldg(a.xcol + j + 3);
+                    }
+                    w[c4 * 4 + 0] = __float_as_uint(x.x); w[c4 * 4 + 1] = __float_as_uint(x.y);
+                    w[c4 * 4 + 2] = __float_as_uint(x.z); w[c4 * 4 + 3] = __float_as_uint(x.w);
+                }
+                tmem_st32(lane_base + (uint32_t)(acc * TN + half * 32), w);
+            }
+        };
         // two-deep prefetch: tile id of visit i + 2, bound terms of visit i + 1 (latency off the critical path)
         int t_cur = n_my > 0 ? tile_of(0) : 0, t_nxt = n_my > 1 ? tile_of(1) : 0;
+        if (XI && n_my > 0) {
+#pragma unroll
+            for (int mr = 0; mr < MR; ++mr) init_acc(mr, t_cur);
+            tmem_st_wait();
+            fence_before();
+            __syncwarp();
+            if (lane == 0)
+                for (int mr = 0; mr < MR; ++mr) mbar_arrive(bar_tempty + 8 * mr);
+        }
         float tn_cur = n_my > 0 ? __ldg(a.tile_inorm + t_cur) : 0.f;
         float tcol_cur = (KXT && n_my > 0) ? __ldg(a.tile_col + t_cur) : 0.f;
         for (int i = 0; i < n_my; ++i) {
@@ -702,7 +743,8 @@ __global__ void __launch_bounds__(tc::NT, 1) tc_sweep_kernel(const __grid_consta
                 tmem_ld32(tbase, va);
                 tmem_ld32(tbase + 32, vb);
                 tmem_ld_wait();
-                // both chunks are in registers: hand the accumulator back to the MMA warp
+                // both chunks are in registers: (XI: write the next tile's x_j into the accumulator,) hand it back to the MMA warp
+                if (XI && i + 1 < n_my) { init_acc(acc, t_cur); tmem_st_wait(); }
                 fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
@@ -1398,8 +1440,8 @@ template <int PASS, int KBLK, int KXT, int MR, int TS>
 static int launch_sweep_t(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p, int m_tiles, cudaStream_t st) {
     using namespace tc;
     const int kblocks = s.d / KB;
-    const size_t a_bytes = TS ? 0 : ((size_t)A_KB_BYTES * kblocks + (s.kx ? A_KX_BYTES : 0)) * MR;
-    const size_t b_bytes = (size_t)B_KB_BYTES * kblocks + (s.kx ? B_KX_BYTES : 0);
+    const size_t a_bytes = TS ? 0 : ((size_t)A_KB_BYTES * kblocks + (KXT == 1 ? A_KX_BYTES : 0)) * MR;
+    const size_t b_bytes = (size_t)B_KB_BYTES * kblocks + (KXT == 1 ? B_KX_BYTES : 0);
     const size_t fixed = 1024 + 256 + 64;
     int n_stages = (int)((227 * 1024 - fixed - a_bytes) / b_bytes);
     if (n_stages > 8) n_stages = 8;
@@ -1417,6 +1459,10 @@ static int launch_sweep(const SweepMaps& tm, const SweepArgs& s, const TcPlan& p
     if (p.ts) {      // user tiles in tensor memory: 3 per CTA
         if (s.d == 64) return s.kx ? launch_sweep_t<PASS, 1, 1, 3, 1>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 1, 0, 3, 1>(tm, s, p, m_tiles, st);
         return s.kx ? launch_sweep_t<PASS, 2, 1, 3, 1>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 2, 0, 3, 1>(tm, s, p, m_tiles, st);
+    }
+    if (s.kx && s.xinit) {   // x_j written into the accumulators by the epilogue warps: no extra K block
+        if (s.d == 64) return launch_sweep_t<PASS, 1, 2, 4, 0>(tm, s, p, m_tiles, st);
+        return launch_sweep_t<PASS, 2, 2, 4, 0>(tm, s, p, m_tiles, st);
     }
     if (s.d == 64) return s.kx ? launch_sweep_t<PASS, 1, 1, 4, 0>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 1, 0, 4, 0>(tm, s, p, m_tiles, st);
     return s.kx ? launch_sweep_t<PASS, 2, 1, 4, 0>(tm, s, p, m_tiles, st) : launch_sweep_t<PASS, 2, 0, 4, 0>(tm, s, p, m_tiles, st);
@@ -1468,6 +1514,7 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
     }
     memset(s, 0, sizeof(*s));
     s->M = a.M; s->N = a.N; s->M_pad = p.M_pad; s->d = a.d; s->kx = kx; s->n_tiles = p.n_tiles;
+    s->xcol = xcol; s->xinit = (kx && !p.ts && env_int("PDA_TC_XINIT", 1)) ? 1 : 0;
     s->tiles_per_split = p.tiles_per_split; s->se = p.se;
     s->n_sel = p.n_sel; s->pos_per_split = (p.n_sel + p.splits - 1) / p.splits;
     s->order = p.ordered ? (const int32_t*)(b + p.o_torder) : nullptr;
