@@ -487,8 +487,9 @@ __device__ __forceinline__ void scan_chunk(const uint32_t (&v)[32], float thr, i
 
 // KBLK = d / 64 K blocks; MR user tiles per CTA; how the column term x_j (pop / bias) enters the accumulator v_j:
 //   KXT = 1: a 16-column extra K block, user side (1,1,1,0..), item side the three bf16 pieces of x_j (one more MMA of 9);
-//   KXT = 2: the epilogue warps WRITE x_j (fp32, exact) into the accumulator with tcgen05.st right after they have read the
-//            previous tile out of it, and every MMA accumulates -- K stays d: 8 MMAs per tile instead of 9 at d = 128;
+//   KXT = 2 (PDA_TC_XINIT=1, experiment): the epilogue warps WRITE x_j (fp32, exact) into the accumulator with tcgen05.st right
+//            after they have read the previous tile out of it, and every MMA accumulates -- 8 MMAs per tile instead of 9 at
+//            d = 128, but the stores serialise against the MMAs in flight (4x slower overall): not the default;
 // TS = 1: the user tiles live in TENSOR memory (tcgen05.mma with the A operand from TMEM): the tensor core then reads
 // only the B tile from shared memory per instruction (64 B/cycle instead of the 128 B/cycle of the shared-memory form
 // at N = 128, which is the whole shared-memory bandwidth of the SM and capped the tensor pipe at ~85 %), and all of the
@@ -1514,7 +1515,9 @@ static int tc_prepare(const EvalArgs& a, char* b, const TcPlan& p, SweepMaps* tm
     }
     memset(s, 0, sizeof(*s));
     s->M = a.M; s->N = a.N; s->M_pad = p.M_pad; s->d = a.d; s->kx = kx; s->n_tiles = p.n_tiles;
-    s->xcol = xcol; s->xinit = (kx && !p.ts && env_int("PDA_TC_XINIT", 1)) ? 1 : 0;
+    // measured (65536 x 1M, d=128): the tcgen05.st writes serialise against the MMAs in flight -- pass B 40.9 ms vs 10.7 ms with
+    // the extra K block; correct (the whole eval suite passes with it) but off by default
+    s->xcol = xcol; s->xinit = (kx && !p.ts && env_int("PDA_TC_XINIT", 0)) ? 1 : 0;
     s->tiles_per_split = p.tiles_per_split; s->se = p.se;
     s->n_sel = p.n_sel; s->pos_per_split = (p.n_sel + p.splits - 1) / p.splits;
     s->order = p.ordered ? (const int32_t*)(b + p.o_torder) : nullptr;

@@ -268,3 +268,18 @@ def test_recommend_tensor_large_item_set_sampled_pass(pda, c_oracle, rec_type, m
     ids = m.do_recommendation(users, None, rec_type, pos_pop=pop, K=K, backend="tensor")
     assert np.array_equal(ids, rid) and m.tc_last_stats()["tile_stride"] == 12
     m.close()
+
+
+def test_recommend_tensor_with_accumulator_preinit_variant(pda, c_oracle, monkeypatch):
+    """PDA_TC_XINIT=1: the column term (pop / bias) written into the TMEM accumulators by the epilogue warps instead of the
+    extra K block (an experiment kept for the record: correct, slower) -- same ids and score bits."""
+    monkeypatch.setenv("PDA_TC_XINIT", "1")
+    m, U, I, indptr, items, pop, rng = _setup(pda, 500, 9000, 128, seed=41, scale=3.0)
+    users = rng.permutation(500)[:490].astype(np.int32)
+    bias = rng.normal(0, 0.3, 9000).astype(np.float32)
+    for rec_type, kw in (("condition", dict(pos_pop=pop)), ("main_branch", dict(col_bias=bias))):
+        ids, sc = m.do_recommendation(users, None, rec_type, K=50, backend="tensor", return_scores=True, **kw)
+        rid, rsc = c_oracle.recommend(U, I, users, rec_type, 50, indptr, items, pop=kw.get("pos_pop"), col_bias=kw.get("col_bias"))
+        assert np.array_equal(ids, rid), rec_type
+        assert np.array_equal(bits(sc), bits(rsc)), rec_type
+    m.close()
