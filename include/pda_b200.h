@@ -204,6 +204,11 @@ int pda_adam_dense_rows_ext(pda_model* m, int which, int64_t row_lo, int64_t row
  * (multimem.ld_reduce sums the accumulators of all ranks in the switch, multimem.st writes the updated rows to every
  * replica).  The caller brackets it with two cross-rank barriers on `stream` and zeroes the accumulator afterwards. */
 int pda_adopt_item_buffers(pda_model* m, float* W_ext, float* G_ext);
+/* cross-rank barriers inside the exchange kernels: flags_local / peer_flags[r] = 64 zero-initialised uint32 per rank in
+ * symmetric memory (peer_flags[r] = rank r's flags as mapped in this process, self included).  Once set, the kernel itself
+ * waits for every rank at its start and completes only when every rank's writes have landed: no barrier launches around
+ * it.  flags_local == NULL switches the in-kernel barriers off again. */
+int pda_dp_set_barrier(pda_model* m, uint32_t* flags_local, uint32_t* const* peer_flags, int32_t world, int32_t rank);
 /* switch the accumulator to another caller-owned ZERO-filled buffer (double buffering; after pda_adopt_item_buffers) */
 int pda_set_item_grad_buffer(pda_model* m, float* G_ext);
 int pda_dp_exchange_adam(pda_model* m, const float* mcG, float* mcW, int64_t row_lo, int64_t row_hi, void* stream);

@@ -68,6 +68,7 @@ PROTOTYPES = {
     "pda_adam_dense_rows": (C.c_int, [c_vp, C.c_int, C.c_int64, C.c_int64, c_vp]),
     "pda_adopt_item_buffers": (C.c_int, [c_vp, c_vp, c_vp]),
     "pda_dp_exchange_adam_p2p": (C.c_int, [c_vp, c_vp, c_vp, C.c_int32, C.c_int32, C.c_int64, C.c_int64, c_vp]),
+    "pda_dp_set_barrier": (C.c_int, [c_vp, c_vp, c_vp, C.c_int32, C.c_int32]),
     "pda_set_item_grad_buffer": (C.c_int, [c_vp, c_vp]),
     "pda_dp_exchange_adam": (C.c_int, [c_vp, c_vp, c_vp, C.c_int64, C.c_int64, c_vp]),
     "pda_stage_batch_host": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, C.c_int64, c_vp]),

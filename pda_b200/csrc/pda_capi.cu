@@ -52,6 +52,7 @@ struct pda_model {
     int item_ext;                      // W[1] / G[1] live in caller-owned (symmetric) memory: not freed here
     // deterministic duplicate-row accumulation (pda_segsum.cu): slot buffer [3 B, d], sort work arrays, cub temp storage
     int deterministic;
+    DpSync dp_sync;                    // in-kernel barriers of the fused exchange (pda_dp_set_barrier)
     void* gslots; size_t gslots_bytes; void* seg_work; size_t seg_work_bytes; void* seg_temp; size_t seg_temp_bytes;
     float* pw;          // {beta1_power, beta2_power}
     double* loss_acc;   // {sum log(sigmoid+1e-10), sum of squares}
@@ -764,6 +765,20 @@ int pda_adopt_item_buffers(pda_model* m, float* W_ext, float* G_ext) {
     return PDA_OK;
 }
 
+// Cross-rank barriers INSIDE the fused exchange kernels: flags = 64 zero-initialised uint32 per rank in symmetric memory
+// (flags_local = this rank's, peer_flags[r] = rank r's as mapped here, self included).  With this set the callers of
+// pda_dp_exchange_adam[_p2p] no longer bracket the kernel with barriers of their own: the kernel waits at its start until
+// every rank has reached it and completes only when every rank's writes have landed.  flags_local == NULL switches it off.
+int pda_dp_set_barrier(pda_model* m, uint32_t* flags_local, uint32_t* const* peer_flags, int32_t world, int32_t rank) {
+    if (!m) return fail(PDA_ERR_ARG, "null model");
+    memset(&m->dp_sync, 0, sizeof(m->dp_sync));
+    if (!flags_local) return PDA_OK;
+    if (!peer_flags || world < 1 || world > 8 || rank < 0 || rank >= world) return fail(PDA_ERR_ARG, "bad argument");
+    m->dp_sync.local = flags_local; m->dp_sync.world = world; m->dp_sync.rank = rank; m->dp_sync.epoch = 0;
+    for (int r = 0; r < world; ++r) m->dp_sync.peer[r] = peer_flags[r];
+    return PDA_OK;
+}
+
 // Point the item-gradient accumulator at another caller-owned, ZERO-filled [n_items, d] buffer (double buffering: the
 // previous one is zeroed off the critical path while the next step accumulates into this one).
 int pda_set_item_grad_buffer(pda_model* m, float* G_ext) {
@@ -786,8 +801,9 @@ int pda_dp_exchange_adam(pda_model* m, const float* mcG, float* mcW, int64_t row
     CK(cudaSetDevice(m->cfg.device));
     const size_t off = (size_t)row_lo * m->d;
     { ProfScope ps(m, PDA_PROF_ADAM, (cudaStream_t)stream);
+      if (m->dp_sync.local) ++m->dp_sync.epoch;
       launch_dp_exchange_adam(mcG + off, mcW + off, m->G[1] + off, m->W[1] + off, m->Mo[1] + off, m->Vo[1] + off, (row_hi - row_lo) * m->d / 4, m->pw,
-                              m->cfg.lr, (cudaStream_t)stream); }
+                              m->cfg.lr, &m->dp_sync, (cudaStream_t)stream); }
     CK(cudaGetLastError());
     return PDA_OK;
 }
@@ -804,8 +820,9 @@ int pda_dp_exchange_adam_p2p(pda_model* m, const float* const* peer_G, float* co
     CK(cudaSetDevice(m->cfg.device));
     const size_t off = (size_t)row_lo * m->d;
     { ProfScope ps(m, PDA_PROF_ADAM, (cudaStream_t)stream);
+      if (m->dp_sync.local) ++m->dp_sync.epoch;
       launch_dp_exchange_adam_p2p(peer_G, peer_W, world, self, (int64_t)off, m->Mo[1] + off, m->Vo[1] + off, (row_hi - row_lo) * m->d / 4,
-                                  m->pw, m->cfg.lr, (cudaStream_t)stream); }
+                                  m->pw, m->cfg.lr, &m->dp_sync, (cudaStream_t)stream); }
     CK(cudaGetLastError());
     return PDA_OK;
 }

@@ -40,6 +40,57 @@ __device__ __forceinline__ float4 multimem_ld_reduce_add_weak(const float* mc) {
     return v;
 }
 
+// ---- cross-rank barriers INSIDE the exchange kernel (flags in symmetric memory; replaces two barrier launches) ----
+// flags of a rank: [0..7] start flags written by rank r, [8..15] end flags written by rank r, [16] grid completion counter
+// (local), [17] time-out marker.  `epoch` increases by one per launch on every rank.
+struct DpBarrier {
+    uint32_t* local;        // this rank's flags (nullptr: the caller brackets the kernel with its own barriers)
+    uint32_t* peer[8];      // every rank's flags as mapped here, self included
+    uint32_t epoch;
+    int world, rank;
+};
+__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// wait until flag >= epoch (epochs are monotonic, compared as a signed distance); ~2 s time-out marks flags[17] instead of hanging
+__device__ __forceinline__ void dp_spin(const uint32_t* flag, uint32_t epoch, uint32_t* timeout_mark) {
+    const long long t0 = clock64();
+    while ((int32_t)(ld_acquire_sys_u32(flag) - epoch) < 0) {
+        if (clock64() - t0 > 4000000000ll) { *timeout_mark = 1u; break; }
+        __nanosleep(64);
+    }
+}
+// every rank's previous kernels on this stream (the step kernel) are complete before any CTA here goes on
+__device__ __forceinline__ void dp_barrier_enter(const DpBarrier& b) {
+    if (!b.local) return;
+    if (blockIdx.x == 0 && threadIdx.x < b.world) st_release_sys_u32(b.peer[threadIdx.x] + b.rank, b.epoch);
+    if (threadIdx.x < b.world) dp_spin(b.local + threadIdx.x, b.epoch, b.local + 17);
+    __syncthreads();
+}
+// the LAST CTA of the grid (all others have fenced and left) tells every rank that this rank's writes have landed and its
+// reads are done, and leaves only when every rank has said the same -- the kernel's completion is the barrier
+__device__ __forceinline__ void dp_barrier_leave(const DpBarrier& b) {
+    if (!b.local) return;
+    __shared__ int s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        s_last = atomicAdd(b.local + 16, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    if (threadIdx.x == 0) { b.local[16] = 0u; __threadfence_system(); }
+    if (threadIdx.x < b.world) {
+        st_release_sys_u32(b.peer[threadIdx.x] + 8 + b.rank, b.epoch);
+        dp_spin(b.local + 8 + threadIdx.x, b.epoch, b.local + 17);
+    }
+}
+
 __device__ __forceinline__ void adam_elem_x(float& w, float& m, float& v, float g, float lr_t) {
     const float omb1 = fsub(1.0f, 0.9f), omb2 = fsub(1.0f, 0.999f);
     m = fadd(fmul(m, 0.9f), fmul(g, omb1));
@@ -55,7 +106,8 @@ template <int U>
 __global__ void __launch_bounds__(256) dp_exchange_adam_kernel(const float* __restrict__ mcG, float* __restrict__ mcW,
                                                                const float* __restrict__ Gl, float* __restrict__ W, float* __restrict__ M,
                                                                float* __restrict__ V, int64_t n4, const float* __restrict__ pw, float lr,
-                                                               int dbg) {
+                                                               int dbg, DpBarrier bar) {
+    dp_barrier_enter(bar);
     const float lr_t = fdiv(fmul(lr, fsqrt(fsub(1.0f, pw[1]))), fsub(1.0f, pw[0]));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n4; base += stride) {
@@ -82,6 +134,7 @@ __global__ void __launch_bounds__(256) dp_exchange_adam_kernel(const float* __re
             else reinterpret_cast<float4*>(W)[e] = w;
         }
     }
+    dp_barrier_leave(bar);
 }
 
 // The same fused exchange over UNICAST peer pointers (symmetric memory, no multicast): the owner of a slice loads the
@@ -112,7 +165,8 @@ __device__ __forceinline__ void st_weak_f4(float* p, const float4& v) {
 template <int U>
 __global__ void __launch_bounds__(256) dp_exchange_adam_p2p_kernel(PeerPtrs pp, int world, int self, float* __restrict__ M,
                                                                    float* __restrict__ V, int64_t n4, const float* __restrict__ pw,
-                                                                   float lr, int mode) {
+                                                                   float lr, int mode, DpBarrier bar) {
+    dp_barrier_enter(bar);
     const float lr_t = fdiv(fmul(lr, fsqrt(fsub(1.0f, pw[1]))), fsub(1.0f, pw[0]));
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * U;
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x * U + threadIdx.x; base < n4; base += stride) {
@@ -143,6 +197,7 @@ __global__ void __launch_bounds__(256) dp_exchange_adam_p2p_kernel(PeerPtrs pp, 
             for (int r = 0; r < world; ++r) { if (mode & 2) st_weak_f4(pp.W[r] + 4 * e, w); else st_sys_f4(pp.W[r] + 4 * e, w); }
         }
     }
+    dp_barrier_leave(bar);
 }
 
 static int env_i(const char* name, int dflt) {
@@ -150,21 +205,34 @@ static int env_i(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+static DpBarrier make_bar(const DpSync* sy) {
+    DpBarrier b;
+    b.local = nullptr; b.epoch = 0; b.world = 0; b.rank = 0;
+    for (int r = 0; r < 8; ++r) b.peer[r] = nullptr;
+    if (sy && sy->local) {
+        b.local = sy->local; b.epoch = sy->epoch; b.world = sy->world; b.rank = sy->rank;
+        for (int r = 0; r < sy->world && r < 8; ++r) b.peer[r] = sy->peer[r];
+    }
+    return b;
+}
+
 void launch_dp_exchange_adam(const float* mcG, float* mcW, const float* Gl, float* W, float* M, float* V, int64_t n4,
-                             const float* pw, float lr, cudaStream_t st) {
+                             const float* pw, float lr, const DpSync* sy, cudaStream_t st) {
+    const DpBarrier bar = make_bar(sy);
     const int U = env_i("PDA_DPX_UNROLL", 2), dbg = env_i("PDA_DPX_DBG", 3);
     int64_t blocks = (n4 + 256 * U - 1) / (256 * U);
     const int cap = env_i("PDA_DPX_BLOCKS", 148 * 2);     // measured at 8 GPUs: 148-296 CTAs x unroll 2 -> 1.08 ms, 592 x 4 -> 1.13 ms
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (U == 1) dp_exchange_adam_kernel<1><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg);
-    else if (U == 2) dp_exchange_adam_kernel<2><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg);
-    else if (U == 8) dp_exchange_adam_kernel<8><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg);
-    else dp_exchange_adam_kernel<4><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg);
+    if (U == 1) dp_exchange_adam_kernel<1><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg, bar);
+    else if (U == 2) dp_exchange_adam_kernel<2><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg, bar);
+    else if (U == 8) dp_exchange_adam_kernel<8><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg, bar);
+    else dp_exchange_adam_kernel<4><<<(int)blocks, 256, 0, st>>>(mcG, mcW, Gl, W, M, V, n4, pw, lr, dbg, bar);
 }
 
 void launch_dp_exchange_adam_p2p(const float* const* G, float* const* W, int world, int self, int64_t off, float* M, float* V,
-                                 int64_t n4, const float* pw, float lr, cudaStream_t st) {
+                                 int64_t n4, const float* pw, float lr, const DpSync* sy, cudaStream_t st) {
+    const DpBarrier bar = make_bar(sy);
     PeerPtrs pp;
     for (int r = 0; r < 8; ++r) { pp.G[r] = r < world ? G[r] + off : nullptr; pp.W[r] = r < world ? W[r] + off : nullptr; }
     const int U = env_i("PDA_DPX_UNROLL", 2), mode = env_i("PDA_DPX_P2P_MODE", 0);
@@ -173,10 +241,10 @@ void launch_dp_exchange_adam_p2p(const float* const* G, float* const* W, int wor
     const int cap = env_i("PDA_DPX_BLOCKS", 148 * 8);
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    if (U == 1) dp_exchange_adam_p2p_kernel<1><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode);
-    else if (U == 4) dp_exchange_adam_p2p_kernel<4><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode);
-    else if (U == 8) dp_exchange_adam_p2p_kernel<8><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode);
-    else dp_exchange_adam_p2p_kernel<2><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode);
+    if (U == 1) dp_exchange_adam_p2p_kernel<1><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode, bar);
+    else if (U == 4) dp_exchange_adam_p2p_kernel<4><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode, bar);
+    else if (U == 8) dp_exchange_adam_p2p_kernel<8><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode, bar);
+    else dp_exchange_adam_p2p_kernel<2><<<(int)blocks, 256, 0, st>>>(pp, world, self, M, V, n4, pw, lr, mode, bar);
 }
 
 }  // namespace pda

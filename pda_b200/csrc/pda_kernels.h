@@ -92,13 +92,15 @@ int launch_bpr_step_pipe(const StepArgs& a, cudaStream_t st);   // pda_step_pipe
 void launch_adam_dense(const AdamArgs& a, cudaStream_t st);
 void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float* pw, int64_t B, float regs,
                         int batch_size, int advance_powers, float lr, float* lr_slot, cudaStream_t st);
+// cross-rank barrier state of the fused exchange kernels (flags in symmetric memory; local == nullptr: none)
+struct DpSync { uint32_t* local; uint32_t* peer[8]; uint32_t epoch; int world, rank; };
 void launch_dp_exchange_adam(const float* mcG, float* mcW, const float* Gl, float* W, float* M, float* V, int64_t n4,
-                             const float* pw, float lr, cudaStream_t st);   // pda_exchange.cu
+                             const float* pw, float lr, const DpSync* sy, cudaStream_t st);   // pda_exchange.cu
 size_t segsum_temp_bytes(int64_t n);
 int launch_segment_sum(const int32_t* a, const int32_t* b, int64_t B, const float* rows, int d, float* G, int32_t* work, void* temp,
                        size_t temp_bytes, int key_bits, cudaStream_t st);   // pda_segsum.cu
 void launch_dp_exchange_adam_p2p(const float* const* G, float* const* W, int world, int self, int64_t off, float* M, float* V,
-                                 int64_t n4, const float* pw, float lr, cudaStream_t st);
+                                 int64_t n4, const float* pw, float lr, const DpSync* sy, cudaStream_t st);
 int launch_adam_lazy_rows(const LazyArgs& a, int phase, cudaStream_t st);
 void launch_adam_lazy_flush(const LazyArgs& a, int tbl, int64_t n_rows, cudaStream_t st);
 void launch_batch_check(const int32_t* users, const int32_t* pos, const int32_t* neg, int64_t B, int32_t n_users,

@@ -292,6 +292,15 @@ class PDAModel:
         """item table + item-gradient accumulator move into caller-owned device memory (symmetric / multicast-mapped)"""
         check(self.lib.pda_adopt_item_buffers(self._h, ptr(int(W_ptr)), ptr(int(G_ptr))))
 
+    def dp_set_barrier(self, flags_local, peer_flags, rank):
+        """in-kernel cross-rank barriers of the fused exchange (flags in symmetric memory); flags_local = 0 switches them off"""
+        if not flags_local:
+            check(self.lib.pda_dp_set_barrier(self._h, None, None, 0, 0))
+            return
+        w = len(peer_flags)
+        arr = (C.c_void_p * w)(*[int(x) for x in peer_flags])
+        check(self.lib.pda_dp_set_barrier(self._h, ptr(int(flags_local)), C.cast(arr, C.c_void_p), w, int(rank)))
+
     def set_item_grad_buffer(self, G_ptr):
         check(self.lib.pda_set_item_grad_buffer(self._h, ptr(int(G_ptr))))
 

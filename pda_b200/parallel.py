@@ -139,6 +139,7 @@ class ShardedTrainer:
     def _setup_nvls(self, dev, need_multicast=True):
         """item table + item-gradient accumulator into symmetric memory with a multicast mapping (torch plumbing); None when
         the platform has no NVLink multicast.  Collective: every rank calls it."""
+        import os
         import torch
         import torch.distributed as dist
         m = self.model
@@ -150,7 +151,7 @@ class ShardedTrainer:
                 symm.enable_symm_mem_for_group(dist.group.WORLD.group_name)
             except Exception:
                 pass
-            buf = symm.empty(3 * n, dtype=torch.float32, device=dev)      # [W | G0 | G1]: the accumulator is double-buffered
+            buf = symm.empty(3 * n + 64, dtype=torch.float32, device=dev)      # [W | G0 | G1 | 64 barrier flags]: accumulator double-buffered
             hdl = symm.rendezvous(buf, dist.group.WORLD)
             mc = int(hdl.multicast_ptr)
             if mc == 0 and need_multicast:
@@ -169,7 +170,14 @@ class ShardedTrainer:
         buf = st["buf"]
         buf[n:].zero_()
         torch.cuda.synchronize()
+        st["hdl"].barrier(channel=0)              # every rank's flags are zero before anyone signals
+        torch.cuda.synchronize()
         m.adopt_item_buffers(buf.data_ptr(), buf.data_ptr() + 4 * n)
+        # cross-rank barriers inside the exchange kernel (flags in the symmetric buffer) instead of two barrier launches
+        st["inkernel"] = os.environ.get("PDA_DP_INKERNEL_BARRIER", "1") != "0"
+        if st["inkernel"]:
+            m.dp_set_barrier(buf.data_ptr() + 12 * n, [x + 12 * n for x in st["peerW"]], self.rank)
+        st["flags"] = buf[3 * n:].view(torch.int32)
         self._wi = buf[:n].view(m.n_items, m.emb_dim)
         st["G"] = [buf[n:2 * n].view(m.n_items, m.emb_dim), buf[2 * n:].view(m.n_items, m.emb_dim)]
         self._gi = st["G"][0]
@@ -212,6 +220,8 @@ class ShardedTrainer:
         n = min(len(p["fwd"]), len(p["rs"]), len(p["adam"]), len(p["ag"]))
         out = {"steps": n, "exchange": self.exchange, "chunks": self.nch, "two_communicators": getattr(self, "_pg_ag", None) is not None}
         if self.exchange in ("nvls", "p2p"):
+            out["in_kernel_barriers"] = bool(self._nvls["inkernel"])
+            out["barrier_timeouts"] = int(self._nvls["flags"][17].item())
             out["phases"] = ("rs_exposed = barrier + fused multimem kernel (the other accumulator is zeroed under it), "
                              "adam_after_rs = second barrier, ag_exposed = 0 (nothing left on the critical path)")
         out["rs_exposed_ms"] = sum(p["fwd"][i].elapsed_time(p["rs"][i]) for i in range(n)) / n
@@ -239,7 +249,8 @@ class ShardedTrainer:
             h, cur = nv["hdl"], nv["cur"]
             wacc = self._async_reduce(self._acc)
             m.adam_apply(stream, part=1)
-            h.barrier(channel=0)                  # every rank's step kernel is done: the accumulators are complete
+            if not nv["inkernel"]:
+                h.barrier(channel=0)              # every rank's step kernel is done: the accumulators are complete
             if cs is not None:
                 # the OTHER accumulator (step k-1's, fully read by every rank since that step's second barrier) is zeroed on a
                 # side stream under this NVLink-bound kernel; the next step accumulates into it
@@ -255,7 +266,8 @@ class ShardedTrainer:
             else:
                 m.dp_exchange_adam(nv["mcG"][cur], nv["mcW"], lo, hi, stream)
             self._mark("rs")
-            h.barrier(channel=1)                  # every replica written, every accumulator read
+            if not nv["inkernel"]:
+                h.barrier(channel=1)              # every replica written, every accumulator read
             self._mark("adam")
             nv["cur"] = 1 - cur
             self._gi = nv["G"][1 - cur]
