@@ -179,7 +179,7 @@ class ShardedTrainer:
             m.dp_set_barrier(buf.data_ptr() + 12 * n, [x + 12 * n for x in st["peerW"]], self.rank)
         st["flags"] = buf[3 * n:].view(torch.int32)
         self._wi = buf[:n].view(m.n_items, m.emb_dim)
-        st["G"] = [buf[n:2 * n].view(m.n_items, m.emb_dim), buf[2 * n:].view(m.n_items, m.emb_dim)]
+        st["G"] = [buf[n:2 * n].view(m.n_items, m.emb_dim), buf[2 * n:3 * n].view(m.n_items, m.emb_dim)]
         self._gi = st["G"][0]
         return st
 

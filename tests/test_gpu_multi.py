@@ -42,7 +42,7 @@ def _worker(rank, world, port, q, adam_mode, exchange):
         try:
             tr = ShardedTrainer(m, world, rank, exchange=exchange)     # "nvls": the fused NVLink-multicast kernel
         except RuntimeError as e:
-            if exchange not in ("nvls", "p2p"):
+            if exchange not in ("nvls", "p2p") or "not available" not in str(e):
                 raise
             q.put((rank, "skip", str(e)))
             return
