@@ -296,7 +296,8 @@ int pda_evaluate_matrix_host(const float* rating_matrix, int32_t rating_len, int
  *   kind 3: every fp32 bit pattern in [lo_or_seed, hi] through the straight-line sqrt refinement vs __fsqrt_rn
  *   kind 0: per_thread x 2 x 303104 random in-range (a, b) pairs through the straight-line quotient vs __fdiv_rn
  *   kind 1 / 2: per_thread x 4 x 303104 random in-range elements through one packed zero-gradient / gradient Adam step
- *               vs the generic separately rounded form (pda_common.cuh) */
+ *               vs the generic separately rounded form (pda_common.cuh)
+ *   kind 4: the same for three consecutive zero-gradient steps in the negated-v form the pipelined step kernel replays with */
 int pda_debug_numerics(int kind, uint32_t lo_or_seed, uint32_t hi, uint64_t per_thread, uint64_t* out5);
 
 #ifdef __cplusplus

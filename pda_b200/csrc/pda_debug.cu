@@ -58,6 +58,7 @@ __device__ __forceinline__ float rnd_float(uint32_t r_m, uint32_t r_e, int e_lo,
 // kind 0: div_rn_inrange(a, b) vs __fdiv_rn, |a| in [2^-100, 2^60], b in [2^-27, 2^21] (the divisor sqrt(v) + eps)
 // kind 1: one zero-gradient step of four elements, unguarded packed form vs the generic intrinsics (w, m, v, lr in range)
 // kind 2: one gradient step of four elements, lazy_grad_step4 vs lazy_grad_step
+// kind 4: three zero-gradient steps on the negated-v state (zero_grad_step4_nv, as lazy_replay4_warp runs them) vs the generic intrinsics
 __global__ void __launch_bounds__(256) random_check_kernel(int kind, uint32_t seed, uint64_t per_thread, DbgOut* o) {
     unsigned long long n = 0, bad = 0;
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -87,7 +88,16 @@ __global__ void __launch_bounds__(256) random_check_kernel(int kind, uint32_t se
             v.z = rnd_float(r2.w[2], r3.w[1] * 7u, ev, ev + 6, false); v.w = rnd_float(r2.w[3], r3.w[1] * 9u, ev, ev + 6, false);
             const float lr = rnd_float(r3.w[0] * 11u, r3.w[1] * 13u, -28, 8, false);
             float4 w2 = w, m2 = m, v2 = v;
-            if (kind == 1) {
+            if (kind == 4) {
+                if (!replay_block_in_range(m, v)) continue;
+                Row4 r = row4_pack(w, m, v);
+                for (int k = 0; k < 3; ++k) {
+                    zero_grad_step4_nv(r, lr);
+                    lazy_zero_grad_step(w2.x, m2.x, v2.x, lr); lazy_zero_grad_step(w2.y, m2.y, v2.y, lr);
+                    lazy_zero_grad_step(w2.z, m2.z, v2.z, lr); lazy_zero_grad_step(w2.w, m2.w, v2.w, lr);
+                }
+                row4_unpack(r, w, m, v);
+            } else if (kind == 1) {
                 if (!replay_block_in_range(m, v)) continue;
                 zero_grad_step4_unguarded(w, m, v, lr);
                 lazy_zero_grad_step(w2.x, m2.x, v2.x, lr); lazy_zero_grad_step(w2.y, m2.y, v2.y, lr);
@@ -118,7 +128,7 @@ extern "C" int pda_debug_numerics(int kind, uint32_t lo_or_seed, uint32_t hi, ui
     if (cudaMalloc((void**)&d, sizeof(DbgOut)) != cudaSuccess) return PDA_ERR_CUDA;
     cudaMemset(d, 0, sizeof(DbgOut));
     if (kind == 3) sqrt_sweep_kernel<<<148 * 8, 256>>>(lo_or_seed, hi, d);
-    else if (kind >= 0 && kind <= 2) random_check_kernel<<<148 * 8, 256>>>(kind, lo_or_seed, per_thread, d);
+    else if ((kind >= 0 && kind <= 2) || kind == 4) random_check_kernel<<<148 * 8, 256>>>(kind, lo_or_seed, per_thread, d);
     else { cudaFree(d); return PDA_ERR_ARG; }
     DbgOut h;
     cudaError_t e = cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);

@@ -105,8 +105,11 @@ struct Chunk {          // lane l holds triple l of the chunk
 
 // MODE 0: BPRMF, 1: PD / PDG.  FUSE: the user table is kept lazily and the warp applies the user row's Adam update
 // (UMODE 2 of bpr_step_kernel); otherwise the user gradient is stored into GU (UMODE 1).  Users are distinct.
-template <int MODE, bool FUSE, int D, int NW>
-__global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) bpr_step_pipe_kernel(StepArgs a, int64_t seg, int hints) {
+// V: 0 = the round-2a instruction stream (per-lane replay guards, elu evaluated for value and derivative separately),
+//    1 = warp-voted replay guard on the negated-v state + one exp per score.  MINB: resident CTAs per SM the register
+//    budget is cut for.
+template <int MODE, bool FUSE, int D, int NW, int MINB, int V>
+__global__ void __launch_bounds__(NW * 32, MINB) bpr_step_pipe_kernel(StepArgs a, int64_t seg, int hints) {
     using namespace sp;
     constexpr bool POP = MODE == 1;
     constexpr int NR = FUSE ? 5 : 3;
@@ -207,7 +210,10 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) bpr_step_pipe_kernel
             if (FUSE) {
                 // catch up: zero-gradient steps applied[u] .. step_no-1 (a never-touched row has m = v = 0: identity)
                 const int64_t done = __shfl_sync(FULL, cur.done, j);
-                if (done < a.step_no) {
+                if (V == 1) {
+                    if (done < a.step_no && lazy_replay4_warp(u, mu, vu, a.lr_hist, done, a.step_no, lr_ok) && lane == 0)
+                        n_replayed += (unsigned long long)(a.step_no - done);
+                } else if (done < a.step_no) {
                     const bool mine = mu.x != 0.f || mu.y != 0.f || mu.z != 0.f || mu.w != 0.f || vu.x != 0.f || vu.y != 0.f ||
                                       vu.z != 0.f || vu.w != 0.f;
                     if (__any_sync(FULL, mine)) {
@@ -223,19 +229,37 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) bpr_step_pipe_kernel
             sq += u.x * u.x + u.y * u.y + u.z * u.z + u.w * u.w;
             sq += p.x * p.x + p.y * p.y + p.z * p.z + p.w * p.w;
             sq += n.x * n.x + n.y * n.y + n.z * n.z + n.w * n.w;
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-                sp_ = fadd(sp_, __shfl_xor_sync(FULL, sp_, off));
-                sn_ = fadd(sn_, __shfl_xor_sync(FULL, sn_, off));
-            }
             // scalar chain (model_api.py:107-114 / 124-126)
             float x, dp, dn;
-            if (POP) {
-                x = fsub(fmul(elu_p1(sp_), pp), fmul(elu_p1(sn_), pn));
-                dp = fmul(elu_p1_grad(sp_), pp);
-                dn = fmul(elu_p1_grad(sn_), pn);
+            if (V == 1) {
+                // the first butterfly step routes the two sums to the two half-warps (lanes 0-15 finish the positive
+                // item's dot, lanes 16-31 the negative item's: the same additions on the same operands as the two full
+                // butterflies), and elu runs ONCE, on both scores side by side
+                const bool lo = lane < 16;
+                float mine = fadd(lo ? sp_ : sn_, __shfl_xor_sync(FULL, lo ? sn_ : sp_, 16));
+#pragma unroll
+                for (int off = 8; off >= 1; off >>= 1) mine = fadd(mine, __shfl_xor_sync(FULL, mine, off));
+                if (POP) {
+                    const float e = elu_p1(mine), popm = lo ? pp : pn;     // elu_p1_grad(s) == elu_p1(s) for s < 0
+                    const float xs = fmul(e, popm), ds = fmul(mine < 0.0f ? e : 1.0f, popm);
+                    x = fsub(__shfl_sync(FULL, xs, 0), __shfl_sync(FULL, xs, 16));
+                    dp = __shfl_sync(FULL, ds, 0); dn = __shfl_sync(FULL, ds, 16);
+                } else {
+                    x = fsub(__shfl_sync(FULL, mine, 0), __shfl_sync(FULL, mine, 16)); dp = 1.0f; dn = 1.0f;
+                }
             } else {
-                x = fsub(sp_, sn_); dp = 1.0f; dn = 1.0f;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    sp_ = fadd(sp_, __shfl_xor_sync(FULL, sp_, off));
+                    sn_ = fadd(sn_, __shfl_xor_sync(FULL, sn_, off));
+                }
+                if (POP) {
+                    x = fsub(fmul(elu_p1(sp_), pp), fmul(elu_p1(sn_), pn));
+                    dp = fmul(elu_p1_grad(sp_), pp);
+                    dn = fmul(elu_p1_grad(sn_), pn);
+                } else {
+                    x = fsub(sp_, sn_); dp = 1.0f; dn = 1.0f;
+                }
             }
             const float sig = fdiv(1.0f, fadd(1.0f, spec_expf(-x)));
             const float sige = fadd(sig, 1e-10f);
@@ -290,11 +314,11 @@ __global__ void __launch_bounds__(NW * 32, NW == 8 ? 3 : 6) bpr_step_pipe_kernel
     }
 }
 
-template <int MODE, bool FUSE, int D, int NW>
+template <int MODE, bool FUSE, int D, int NW, int MINB, int V>
 static int launch_pipe_inst(const StepArgs& a, int hints, cudaStream_t st) {
     constexpr int NR = FUSE ? 5 : 3;
     const size_t smem = (size_t)NW * D * NR * sp::ROW_B + (size_t)NW * D * 8 + 16;
-    auto kern = bpr_step_pipe_kernel<MODE, FUSE, D, NW>;
+    auto kern = bpr_step_pipe_kernel<MODE, FUSE, D, NW, MINB, V>;
     static int ctas_per_sm = 0, n_sm = 0;
     if (!ctas_per_sm) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
@@ -315,11 +339,23 @@ static int launch_pipe_inst(const StepArgs& a, int hints, cudaStream_t st) {
     return 0;
 }
 
-template <int D, int NW>
+template <int D, int NW, int MINB, int V>
 static int launch_pipe_dn(const StepArgs& a, int hints, cudaStream_t st) {
     const bool fuse = a.fuse_user_adam != 0;
-    if (a.pop_mode == 1) return fuse ? launch_pipe_inst<1, true, D, NW>(a, hints, st) : launch_pipe_inst<1, false, D, NW>(a, hints, st);
-    return fuse ? launch_pipe_inst<0, true, D, NW>(a, hints, st) : launch_pipe_inst<0, false, D, NW>(a, hints, st);
+    if (a.pop_mode == 1)
+        return fuse ? launch_pipe_inst<1, true, D, NW, MINB, V>(a, hints, st) : launch_pipe_inst<1, false, D, NW, MINB, V>(a, hints, st);
+    return fuse ? launch_pipe_inst<0, true, D, NW, MINB, V>(a, hints, st) : launch_pipe_inst<0, false, D, NW, MINB, V>(a, hints, st);
+}
+
+template <int V>
+static int launch_pipe_v(const StepArgs& a, int hints, int D, int NW, cudaStream_t st) {
+    if (NW == 4) {
+        if (D == 2) return launch_pipe_dn<2, 4, 6, V>(a, hints, st);
+        return launch_pipe_dn<3, 4, 6, V>(a, hints, st);
+    }
+    if (D == 2) return launch_pipe_dn<2, 8, 3, V>(a, hints, st);
+    if (D == 4) return launch_pipe_dn<4, 8, 3, V>(a, hints, st);
+    return launch_pipe_dn<3, 8, 3, V>(a, hints, st);
 }
 
 // returns 0 when the pipelined kernel took the launch, non-zero when the shape is not its (the caller falls back)
@@ -333,15 +369,10 @@ int launch_bpr_step_pipe(const StepArgs& a, cudaStream_t st) {
     const int D = e ? atoi(e) : 3;
     e = getenv("PDA_STEP_PIPE_NW");
     const int NW = e ? atoi(e) : 8;
-    if (NW == 4) {
-        if (D == 2) return launch_pipe_dn<2, 4>(a, hints, st);
-        if (D == 4) return launch_pipe_dn<4, 4>(a, hints, st);
-        return launch_pipe_dn<3, 4>(a, hints, st);
-    }
-    if (D == 2) return launch_pipe_dn<2, 8>(a, hints, st);
-    if (D == 4) return launch_pipe_dn<4, 8>(a, hints, st);
-    if (D == 6) return launch_pipe_dn<6, 8>(a, hints, st);
-    return launch_pipe_dn<3, 8>(a, hints, st);
+    // 4 CTAs per SM (28 / 32 warps on a 72 / 64-register budget, ring depth 3 / 2) measured slower: 1.36 / 1.38 vs 1.31 ms
+    e = getenv("PDA_STEP_PIPE_V");
+    const int V = e ? atoi(e) : 1;
+    return V == 0 ? launch_pipe_v<0>(a, hints, D, NW, st) : launch_pipe_v<1>(a, hints, D, NW, st);
 }
 
 }  // namespace pda

@@ -48,10 +48,10 @@ def test_div_refinement_random_2_to_33(pda):
     assert bad == 0, (bad, first)
 
 
-@pytest.mark.parametrize("kind", [1, 2])
+@pytest.mark.parametrize("kind", [1, 2, 4])
 def test_packed_adam_steps_equal_generic_form(pda, kind):
-    """2^31 random in-range elements through zero_grad_step4_unguarded (kind 1) / lazy_grad_step4 (kind 2) vs
-    lazy_zero_grad_step / lazy_grad_step: w, m, v bit-identical"""
+    """2^31 random in-range elements through zero_grad_step4_unguarded (kind 1) / lazy_grad_step4 (kind 2) / three
+    steps of the negated-v form zero_grad_step4_nv (kind 4) vs lazy_zero_grad_step / lazy_grad_step: w, m, v bit-identical"""
     threads = 148 * 8 * 256
     per_thread = (1 << 31) // (4 * threads) + 1
     n, bad, first = _numerics(pda, kind, 777 + kind, 0, per_thread)

@@ -30,13 +30,14 @@ def _distinct_batch(rng, n_users, n_items, B):
 
 @pytest.mark.parametrize("train", ["s_condition", "normal"])
 @pytest.mark.parametrize("adam", ["lazy"])
-@pytest.mark.parametrize("knobs", [{}, {"PDA_STEP_PIPE_D": "2"}, {"PDA_STEP_PIPE_D": "4"}, {"PDA_STEP_PIPE_D": "6"},
-                                   {"PDA_STEP_PIPE_NW": "4"}, {"PDA_STEP_PIPE_HINTS": "0"}, {"PDA_STEP_PIPE_HINTS": "1"}])
+@pytest.mark.parametrize("knobs", [{}, {"PDA_STEP_PIPE_D": "2"}, {"PDA_STEP_PIPE_D": "4"}, {"PDA_STEP_PIPE_V": "0"},
+                                   {"PDA_STEP_PIPE_NW": "4"}, {"PDA_STEP_PIPE_HINTS": "3"},
+                                   {"PDA_STEP_PIPE_NW": "4", "PDA_STEP_PIPE_V": "0"}])
 def test_pipe_kernel_bit_identical_to_register_kernel(pda, monkeypatch, train, adam, knobs):
     """The fused user-row Adam (replay + update in the step kernel; the dense-table variant of the pipelined kernel needs
     the device sampler's distinct-users guarantee and is covered by the oracle test below).  Host batches with distinct users and distinct items -> every table and Adam slot bit-identical after every step,
     ragged sizes (1, 31, 33, 1000, 4097) included; users come back after long lags."""
-    if knobs and train == "normal":
+    if knobs and train == "normal" and knobs != {"PDA_STEP_PIPE_V": "0"}:
         pytest.skip("knob sweep on the main variant only")
     rng = np.random.default_rng(5)
     n_users, n_items, d = 9000, 9000, 128
@@ -106,7 +107,8 @@ def test_pipe_kernel_matches_oracle_with_duplicate_items_and_sampler(pda, c_orac
     m.close()
 
 
-def test_pipe_kernel_generic_path_for_out_of_range_operands(pda, monkeypatch):
+@pytest.mark.parametrize("variant", ["1", "0"])
+def test_pipe_kernel_generic_path_for_out_of_range_operands(pda, monkeypatch, variant):
     """Adam slots outside the guarded ranges (tiny / huge / zero m, v; some lanes zero) take the generic
     __fsqrt_rn / __fdiv_rn path inside the pipelined kernel: still bit-identical to the register kernel and to the
     dense sweep."""
@@ -134,6 +136,7 @@ def test_pipe_kernel_generic_path_for_out_of_range_operands(pda, monkeypatch):
         out = {}
         for name, m in ms.items():
             monkeypatch.setenv("PDA_STEP_PIPE", "0" if name == "reg" else "1")
+            monkeypatch.setenv("PDA_STEP_PIPE_V", variant)      # 1: warp-voted guard + negated-v replay, 0: per-lane guards
             out[name] = m.train_step(*batch)
         assert np.allclose(out["pipe"], out["reg"], rtol=1e-6, atol=0, equal_nan=True), (step, out)
         assert np.allclose(out["pipe"], out["dense"], rtol=1e-6, atol=0, equal_nan=True), (step, out)

@@ -48,7 +48,7 @@ def main():
     if a.variants:
         variants = [dict(kv.split("=") for kv in v.split(",")) for v in a.variants.split(";")]
     for v in variants:
-        for k in ("PDA_STEP_PIPE", "PDA_STEP_PIPE_D", "PDA_STEP_PIPE_NW", "PDA_STEP_PIPE_HINTS"):
+        for k in ("PDA_STEP_PIPE", "PDA_STEP_PIPE_D", "PDA_STEP_PIPE_NW", "PDA_STEP_PIPE_HINTS", "PDA_STEP_PIPE_V"):
             os.environ.pop(k, None)
         os.environ.update(v)
         m.train_sampled(2020, 0, step, 5, B); step += 5
