@@ -45,6 +45,7 @@ PROTOTYPES = {
     "pda_synchronize": (C.c_int, [c_vp]),
     "pda_set_adam_mode": (C.c_int, [c_vp, C.c_int]),
     "pda_set_deterministic": (C.c_int, [c_vp, C.c_int]),
+    "pda_set_hot_items": (C.c_int, [c_vp, c_vp, C.c_int32]),
     "pda_adam_stats": (C.c_int, [c_vp, c_vp, C.c_int]),
     "pda_profile_enable": (C.c_int, [c_vp, C.c_int]),
     "pda_profile_read": (C.c_int, [c_vp, c_vp, c_vp]),

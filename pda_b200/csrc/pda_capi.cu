@@ -64,6 +64,7 @@ struct pda_model {
     int32_t* active; int64_t n_act;
     int32_t* unique_times; int32_t n_times;
     float* pop_train; int32_t T_pop;
+    uint8_t* hot_slot; int32_t* hot_ids; int n_hot;   // popular items of the step kernel (pda_set_hot_items)
     // batch buffers
     int64_t cap, last_B, global_batch;
     int batch_uniq;   // internal batch holds distinct users (device sampler with B <= #active users)
@@ -220,7 +221,7 @@ void pda_destroy(pda_model* m) {
     cudaFreeHost(m->chk_pinned); cudaEventDestroy(m->ev_staged);
     cudaFree(m->pw); cudaFree(m->loss_acc); cudaFree(m->loss3); cudaFree(m->loss_sum); cudaFreeHost(m->loss3_pinned);
     cudaFree(m->indptr); cudaFree(m->items); cudaFree(m->times); cudaFree(m->active); cudaFree(m->unique_times);
-    cudaFree(m->pop_train);
+    cudaFree(m->pop_train); cudaFree(m->hot_slot); cudaFree(m->hot_ids);
     cudaFree(m->b_users); cudaFree(m->b_pos); cudaFree(m->b_neg); cudaFree(m->b_time); cudaFree(m->b_pp); cudaFree(m->b_np);
     if (m->pipe_ready) {
         cudaFree(m->b2_users); cudaFree(m->b2_pos); cudaFree(m->b2_neg); cudaFree(m->b2_pp); cudaFree(m->b2_np);
@@ -394,6 +395,67 @@ int pda_set_deterministic(pda_model* m, int on) {
     return PDA_OK;
 }
 
+// The popular items whose positive-item gradient rows the pipelined step kernel sums per CTA in shared memory before they
+// reach the accumulator (same-row red.global.add serialises in L2).  A performance hint only: any list gives the same sums.
+int pda_set_hot_items(pda_model* m, const int32_t* ids, int32_t n) {
+    if (!m || n < 0 || (n > 0 && !ids)) return fail(PDA_ERR_ARG, "bad argument");
+    if (n > PDA_MAX_HOT_ITEMS) n = PDA_MAX_HOT_ITEMS;
+    for (int32_t i = 0; i < n; ++i) {
+        if (ids[i] < 0 || ids[i] >= m->nI) return fail(PDA_ERR_ARG, "hot item id %d outside [0, %lld)", ids[i], (long long)m->nI);
+        for (int32_t j = 0; j < i; ++j)
+            if (ids[j] == ids[i]) return fail(PDA_ERR_ARG, "hot item id %d listed twice", ids[i]);
+    }
+    CK(cudaSetDevice(m->cfg.device));
+    CK(cudaDeviceSynchronize());
+    m->n_hot = 0;
+    if (n == 0) return PDA_OK;
+    if (!m->hot_slot) {
+        CK(cudaMalloc((void**)&m->hot_slot, (size_t)m->nI));
+        CK(cudaMalloc((void**)&m->hot_ids, sizeof(int32_t) * PDA_MAX_HOT_ITEMS));
+    }
+    uint8_t* h = (uint8_t*)malloc((size_t)m->nI);
+    if (!h) return fail(PDA_ERR_STATE, "out of host memory");
+    memset(h, 255, (size_t)m->nI);
+    for (int32_t i = 0; i < n; ++i) h[ids[i]] = (uint8_t)i;
+    cudaError_t e = cudaMemcpy(m->hot_slot, h, (size_t)m->nI, cudaMemcpyHostToDevice);
+    free(h);
+    if (e != cudaSuccess) return fail(PDA_ERR_CUDA, "cudaMemcpy failed: %s", cudaGetErrorString(e));
+    CK(cudaMemcpy(m->hot_ids, ids, sizeof(int32_t) * (size_t)n, cudaMemcpyHostToDevice));
+    m->n_hot = n;
+    return PDA_OK;
+}
+
+// default hot list: the most frequent items of the train CSR ($PDA_STEP_HOT = how many, 0 = none; at most PDA_MAX_HOT_ITEMS)
+static int hot_items_from_csr(pda_model* m) {
+    const char* e = getenv("PDA_STEP_HOT");
+    int want = e ? atoi(e) : PDA_MAX_HOT_ITEMS;
+    if (want > PDA_MAX_HOT_ITEMS) want = PDA_MAX_HOT_ITEMS;
+    if (want > m->nI) want = (int)m->nI;
+    if (want <= 0 || m->nnz <= 0 || m->d != 128) return pda_set_hot_items(m, nullptr, 0);   // only the d = 128 pipeline uses it
+    int32_t* cnt_d = nullptr;
+    CK(cudaMalloc((void**)&cnt_d, sizeof(int32_t) * (size_t)m->nI));
+    CK(cudaMemset(cnt_d, 0, sizeof(int32_t) * (size_t)m->nI));
+    launch_item_count(m->items, m->nnz, cnt_d, 0);
+    int32_t* cnt = (int32_t*)malloc(sizeof(int32_t) * (size_t)m->nI);
+    if (!cnt) { cudaFree(cnt_d); return fail(PDA_ERR_STATE, "out of host memory"); }
+    cudaError_t ce = cudaMemcpy(cnt, cnt_d, sizeof(int32_t) * (size_t)m->nI, cudaMemcpyDeviceToHost);
+    cudaFree(cnt_d);
+    if (ce != cudaSuccess) { free(cnt); return fail(PDA_ERR_CUDA, "item count failed: %s", cudaGetErrorString(ce)); }
+    int32_t ids[PDA_MAX_HOT_ITEMS];
+    int n = 0;
+    for (int k = 0; k < want; ++k) {        // `want` selection passes over the counts: <= 28 x n_items, once per CSR
+        int64_t best = -1;
+        for (int64_t i = 0; i < m->nI; ++i)
+            if (cnt[i] > 0 && (best < 0 || cnt[i] > cnt[best])) best = i;
+        // an item is worth a shared-memory row only if it repeats inside a batch often: >= ~1 triple in 4096 of the CSR
+        if (best < 0 || (int64_t)cnt[best] * 4096 < m->nnz) break;
+        ids[n++] = (int32_t)best;
+        cnt[best] = 0;
+    }
+    free(cnt);
+    return pda_set_hot_items(m, ids, n);
+}
+
 int pda_set_adam_mode(pda_model* m, int mode) {
     if (!m) return fail(PDA_ERR_ARG, "null model");
     if (mode != PDA_ADAM_DENSE && mode != PDA_ADAM_LAZY && mode != PDA_ADAM_LAZY_USERS)
@@ -474,7 +536,7 @@ int pda_set_train_csr(pda_model* m, const int64_t* indptr, const int32_t* items,
         CK(cudaMemcpy(m->unique_times, unique_times, (size_t)n_times * 4, cudaMemcpyHostToDevice));
         m->n_times = n_times;
     }
-    return PDA_OK;
+    return hot_items_from_csr(m);
 }
 
 int pda_set_train_pop(pda_model* m, const float* pop, int32_t T_pop) {
@@ -513,7 +575,7 @@ int pda_set_train_csr_device(pda_model* m, const int64_t* indptr_d, const int32_
         CK(cudaMemcpy(m->unique_times, unique_times, (size_t)n_times * 4, cudaMemcpyHostToDevice));
         m->n_times = n_times;
     }
-    return PDA_OK;
+    return hot_items_from_csr(m);
 }
 
 static int do_sample(pda_model* m, uint32_t seed, uint32_t epoch, uint32_t step, int64_t B, cudaStream_t st, int slot = 0) {
@@ -602,6 +664,7 @@ static int enqueue_fwd_bwd(pda_model* m, const int32_t* users, const int32_t* po
     }
     s.pop_mode = m->cfg.train_mode == PDA_TRAIN_S_CONDITION ? 1 : m->cfg.train_mode == PDA_TRAIN_TEMP_POP ? 2 : 0;
     s.uniq_users = uniq;
+    s.hot_slot = m->hot_slot; s.hot_ids = m->hot_ids; s.n_hot = m->n_hot;
     if (s.pop_mode == 2) {   // BPR(t)-pop: the stage of each triple rides in the internal batch (b_time)
         if (pp) {   // explicit batch: the reference passes `temp` as fp32 through the pos_pop slot (train_new_api.py:544,565)
             if (B > m->cap) return fail(PDA_ERR_ARG, "B exceeds the batch capacity");

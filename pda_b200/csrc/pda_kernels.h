@@ -37,7 +37,12 @@ struct StepArgs {
     // deterministic mode (pda_segsum.cu): per-triple gradient rows are STORED, slot i = pos row of triple i, B + i = neg
     // row, 2B + i = user row (only when users may repeat); the ordered segment sum fills GU / GI afterwards
     float* Gslots;
+    // popular items (pda_set_hot_items; by default the n_hot most frequent items of the train CSR): hot_slot[item] = slot
+    // 0..n_hot-1 or 255.  The pipelined kernel sums their positive-item gradient rows per CTA in shared memory and adds
+    // each row to GI once per CTA -- the same-row red.global.add traffic of a Zipf head serialises in L2
+    const uint8_t* hot_slot; const int32_t* hot_ids; int n_hot;
 };
+constexpr int PDA_MAX_HOT_ITEMS = 28;   // 14 KB: what a 3-stage ring of 8 warps leaves of a third of an SM's shared memory
 
 struct AdamArgs {
     float* W[4]; float* m[4]; float* v[4]; float* G[4];   // user table, item table, [user bias, item bias]
@@ -88,6 +93,7 @@ void launch_xavier_init(float* W, int64_t rows, int cols, uint32_t seed, uint32_
 void sampler_keys(uint32_t seed, uint32_t epoch, uint32_t step, uint32_t* keys);
 void launch_sampler(SamplerArgs a, cudaStream_t st);
 int launch_bpr_step(const StepArgs& a, cudaStream_t st);
+void launch_item_count(const int32_t* items, int64_t nnz, int32_t* cnt, cudaStream_t st);
 int launch_bpr_step_pipe(const StepArgs& a, cudaStream_t st);   // pda_step_pipe.cu; non-zero = shape not covered
 void launch_adam_dense(const AdamArgs& a, cudaStream_t st);
 void launch_finish_step(double* loss_acc, float* loss3, double* loss_sum, float* pw, int64_t B, float regs,

@@ -16,6 +16,10 @@
 //   * L2 policy: user rows are touched once per step (3.2 GB of the step's traffic on the synthetic set) -> evict_first
 //     on their loads and stores; item rows and the item-gradient accumulator are Zipf-hot -> evict_last, so the hot
 //     head of the item table stays in the 126 MB L2.
+//   * the gradient rows of the n_hot most popular positive items (StepArgs::hot_slot) are summed per CTA in shared memory
+//     (CAS-loop fp32 atomics) and reach the accumulator once per CTA: 2^20 triples put 25 % of their positive-item rows on
+//     28 addresses, and same-address red.global.add serialises in L2 (tools/microbench/gather_bw: 1.14 -> 0.92 ms for the
+//     memory skeleton when those reductions disappear).
 //   * the exact replay runs with one range guard per block of 8 steps (pda_common.cuh), the row's own Adam step with
 //     one guard per float4, log(sigmoid + 1e-10) once per 32 triples (lane l <- triple l).
 #include <stdlib.h>
@@ -97,6 +101,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t addr) {
 
 struct Chunk {          // lane l holds triple l of the chunk
     int32_t iu, ip, in, done;
+    int32_t hs;         // shared-memory slot of a popular positive item, 255 = none
     float pp, pn;
     int n;              // triples in the chunk (0 = no chunk)
 };
@@ -119,6 +124,8 @@ __global__ void __launch_bounds__(NW * 32, MINB) bpr_step_pipe_kernel(StepArgs a
     const uint32_t rows0 = smem_u32(smem) + (uint32_t)(warp * D * STAGE_B);
     const uint32_t bars0 = smem_u32(smem) + (uint32_t)(NW * D * STAGE_B) + (uint32_t)(warp * D * 8);
     int* counter = reinterpret_cast<int*>(smem + NW * D * STAGE_B + NW * D * 8);
+    float* hot_acc = reinterpret_cast<float*>(smem + NW * D * STAGE_B + NW * D * 8 + 16);   // [n_hot][128]
+    for (int i = threadIdx.x; i < a.n_hot * 128; i += NW * 32) hot_acc[i] = 0.0f;
 
     const int64_t t_begin = blockIdx.x * seg;
     const int64_t t_end = t_begin + seg < a.B ? t_begin + seg : a.B;
@@ -147,7 +154,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) bpr_step_pipe_kernel(StepArgs a
     };
     auto load_chunk = [&](int c) -> Chunk {
         Chunk k;
-        k.iu = k.ip = k.in = 0; k.done = 0; k.pp = k.pn = 1.0f; k.n = 0;
+        k.iu = k.ip = k.in = 0; k.done = 0; k.hs = 255; k.pp = k.pn = 1.0f; k.n = 0;
         if (c < 0) return k;
         const int64_t t0 = t_begin + (int64_t)c * 32;
         k.n = t_end - t0 < 32 ? (int)(t_end - t0) : 32;
@@ -156,6 +163,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) bpr_step_pipe_kernel(StepArgs a
             k.iu = __ldg(a.users + t); k.ip = __ldg(a.pos + t); k.in = __ldg(a.neg + t);
             if (POP) { k.pp = __ldg(a.pos_pop + t); k.pn = __ldg(a.neg_pop + t); }
             if (FUSE) k.done = a.appliedU[k.iu];
+            if (a.n_hot) k.hs = __ldg(a.hot_slot + k.ip);
         }
         return k;
     };
@@ -291,13 +299,28 @@ __global__ void __launch_bounds__(NW * 32, MINB) bpr_step_pipe_kernel(StepArgs a
                 float* gu = a.GU + iu * 128 + lane * 4;
                 st_f4_hint(gu, du, pol_user);
             }
-            red_add_f4_hint(gp, dpv, pol_item); red_add_f4_hint(gn, dnv, pol_item);
+            const int hs = a.n_hot ? __shfl_sync(FULL, cur.hs, j) : 255;
+            if (hs < a.n_hot) {
+                float* h = hot_acc + hs * 128 + lane * 4;
+                atomicAdd(h, dpv.x); atomicAdd(h + 1, dpv.y); atomicAdd(h + 2, dpv.z); atomicAdd(h + 3, dpv.w);
+            } else {
+                red_add_f4_hint(gp, dpv, pol_item);
+            }
+            red_add_f4_hint(gn, dnv, pol_item);
         }
         if (lane < cur.n) mf_acc += (double)logf(sige_mine);
         cur = nxt;
         nxt = load_chunk(cur.n == 32 ? grab() : -1);
     }
 
+    if (a.n_hot) {   // every CTA adds its sums of the popular rows once
+        __syncthreads();
+        for (int r = warp; r < a.n_hot; r += NW) {
+            const float4 v = *reinterpret_cast<const float4*>(hot_acc + r * 128 + lane * 4);
+            if (__any_sync(FULL, v.x != 0.f || v.y != 0.f || v.z != 0.f || v.w != 0.f))
+                red_add_f4_hint(a.GI + (int64_t)__ldg(a.hot_ids + r) * 128 + lane * 4, v, pol_item);
+        }
+    }
     if (FUSE) {
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) n_replayed += __shfl_xor_sync(FULL, n_replayed, off);
@@ -317,7 +340,12 @@ __global__ void __launch_bounds__(NW * 32, MINB) bpr_step_pipe_kernel(StepArgs a
 template <int MODE, bool FUSE, int D, int NW, int MINB, int V>
 static int launch_pipe_inst(const StepArgs& a, int hints, cudaStream_t st) {
     constexpr int NR = FUSE ? 5 : 3;
-    const size_t smem = (size_t)NW * D * NR * sp::ROW_B + (size_t)NW * D * 8 + 16;
+    // the popular-item rows take what the ring leaves of the MINB-CTAs-per-SM budget (227 KB - 1 KB reserved per CTA)
+    const size_t ring = (size_t)NW * D * NR * sp::ROW_B + (size_t)NW * D * 8 + 16;
+    const size_t per_cta = (size_t)(227 * 1024) / MINB - 1024;
+    const int hot_cap = per_cta > ring ? (int)((per_cta - ring) / sp::ROW_B) : 0;
+    const int hot_rows = hot_cap < PDA_MAX_HOT_ITEMS ? hot_cap : PDA_MAX_HOT_ITEMS;   // constant per instantiation
+    const size_t smem = ring + (size_t)hot_rows * sp::ROW_B;
     auto kern = bpr_step_pipe_kernel<MODE, FUSE, D, NW, MINB, V>;
     static int ctas_per_sm = 0, n_sm = 0;
     if (!ctas_per_sm) {
@@ -335,7 +363,9 @@ static int launch_pipe_inst(const StepArgs& a, int hints, cudaStream_t st) {
     if (grid < 1) grid = 1;
     const int64_t seg = ((chunks + grid - 1) / grid) * 32;
     grid = (a.B + seg - 1) / seg;
-    kern<<<(int)grid, NW * 32, smem, st>>>(a, seg, hints);
+    StepArgs b = a;
+    if (b.n_hot > hot_rows) b.n_hot = hot_rows;   // slots beyond the shared-memory rows keep the global reduction
+    kern<<<(int)grid, NW * 32, smem, st>>>(b, seg, hints);
     return 0;
 }
 

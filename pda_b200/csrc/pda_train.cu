@@ -319,6 +319,15 @@ static void launch_step_gc(const StepArgs& a, int grid, cudaStream_t st) {
     }
 }
 
+// occurrences of every item in the train CSR (one-time, at pda_set_train_csr*: picks the popular items of StepArgs::hot_slot)
+__global__ void __launch_bounds__(256) item_count_kernel(const int32_t* __restrict__ items, int64_t nnz, int32_t* __restrict__ cnt) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nnz; i += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(cnt + items[i], 1);
+}
+void launch_item_count(const int32_t* items, int64_t nnz, int32_t* cnt, cudaStream_t st) {
+    if (nnz > 0) item_count_kernel<<<148 * 8, 256, 0, st>>>(items, nnz, cnt);
+}
+
 int launch_bpr_step(const StepArgs& a, cudaStream_t st) {
     if (a.d % 4 != 0 || a.d < 4 || a.d > 512) return 1;
     if (launch_bpr_step_pipe(a, st) == 0) return 0;      // d = 128, distinct users: the bulk-copy pipeline (pda_step_pipe.cu)

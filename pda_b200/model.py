@@ -84,6 +84,12 @@ class PDAModel:
         bit-identical to the CPU oracle (about twice the step cost)"""
         check(self.lib.pda_set_deterministic(self._h, 1 if on else 0))
 
+    def set_hot_items(self, ids):
+        """popular items whose positive-item gradient rows the d = 128 step kernel pre-sums per thread block in shared
+        memory (at most 28; a performance hint -- set_train_csr* installs the most frequent items of the CSR)"""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        check(self.lib.pda_set_hot_items(self._h, ptr(ids) if ids.size else None, int(ids.size)))
+
     def adam_stats(self, reset=True):
         """(rows updated with a gradient, zero-gradient row-steps replayed) by the lazy Adam kernels since the last reset."""
         out = np.zeros(2, dtype=np.int64)

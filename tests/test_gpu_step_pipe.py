@@ -32,7 +32,8 @@ def _distinct_batch(rng, n_users, n_items, B):
 @pytest.mark.parametrize("adam", ["lazy"])
 @pytest.mark.parametrize("knobs", [{}, {"PDA_STEP_PIPE_D": "2"}, {"PDA_STEP_PIPE_D": "4"}, {"PDA_STEP_PIPE_V": "0"},
                                    {"PDA_STEP_PIPE_NW": "4"}, {"PDA_STEP_PIPE_HINTS": "3"},
-                                   {"PDA_STEP_PIPE_NW": "4", "PDA_STEP_PIPE_V": "0"}])
+                                   {"PDA_STEP_PIPE_NW": "4", "PDA_STEP_PIPE_V": "0"}, {"hot": "28"}, {"hot": "28", "PDA_STEP_PIPE_NW": "4"},
+                                   {"hot": "5", "PDA_STEP_PIPE_D": "2"}])
 def test_pipe_kernel_bit_identical_to_register_kernel(pda, monkeypatch, train, adam, knobs):
     """The fused user-row Adam (replay + update in the step kernel; the dense-table variant of the pipelined kernel needs
     the device sampler's distinct-users guarantee and is covered by the oracle test below).  Host batches with distinct users and distinct items -> every table and Adam slot bit-identical after every step,
@@ -49,6 +50,9 @@ def test_pipe_kernel_bit_identical_to_register_kernel(pda, monkeypatch, train, a
         m.set_table("user_embedding", U); m.set_table("item_embedding", I)
         m.set_adam_mode(adam)
         ms[name] = m
+    knobs = dict(knobs)
+    if "hot" in knobs:   # popular-item rows pre-summed in shared memory: an item occurs once per batch here -> still the same bits
+        ms["pipe"].set_hot_items(rng.permutation(n_items)[:int(knobs.pop("hot"))])
     sizes = [1000, 1, 31, 33, 4097, 1000, 2, 4096, 64] + [777] * 12
     for step, B in enumerate(sizes):
         batch = _distinct_batch(rng, n_users, n_items, B)
@@ -146,6 +150,48 @@ def test_pipe_kernel_generic_path_for_out_of_range_operands(pda, monkeypatch, va
         assert np.array_equal(bits(a[k]), bits(c[k])), k
     for m in ms.values():
         m.close()
+
+
+@pytest.mark.parametrize("train", ["s_condition", "normal"])
+def test_popular_item_rows_summed_in_shared_memory(pda, c_oracle, train):
+    """A Zipf head on the positive items (half of the batch on 28 items, one item on 10 % of it): the per-CTA shared-memory
+    sums of the popular rows (pda_set_hot_items) give the item gradient of the plain red.global.add path and of the C
+    oracle to 1e-5 of scale (item_m after the first Adam step = 0.1 x gradient), for hot lists of 0 / 5 / 28 items;
+    ids outside the table and repeated ids are rejected."""
+    rng = np.random.default_rng(31)
+    n_users, n_items, d, B = 6000, 2000, 128, 4096
+    U = rng.normal(0, 0.1, (n_users, d)).astype(np.float32)
+    I = rng.normal(0, 0.1, (n_items, d)).astype(np.float32)
+    head = rng.permutation(n_items)[:28].astype(np.int32)
+    users = rng.permutation(n_users)[:B].astype(np.int32)
+    pos = rng.integers(0, n_items, B).astype(np.int32)
+    sel = rng.random(B)
+    pos[sel < 0.5] = head[rng.integers(0, 28, int((sel < 0.5).sum()))]
+    pos[sel < 0.1] = head[0]
+    neg = rng.integers(0, n_items, B).astype(np.int32)
+    pp, pn = rng.random(B).astype(np.float32), rng.random(B).astype(np.float32)
+    batch = (users, pos, neg, pp, pn) if train == "s_condition" else (users, pos, neg)
+    ref = c_oracle.CModel(U, I, 1e-2, 1e-3, B, train)
+    want_loss = ref.train_step(users, pos, neg, pp if train == "s_condition" else None, pn if train == "s_condition" else None)
+    scale = np.abs(ref.mI).max()
+    got = {}
+    for n_hot in (0, 5, 28):
+        m = pda.PDAModel(n_users, n_items, d, train=train, batch_size=B, lr=1e-2, regs=1e-3, init=False, max_batch=B)
+        m.set_table("user_embedding", U); m.set_table("item_embedding", I)
+        m.set_adam_mode("lazy")
+        m.set_hot_items(head[:n_hot])
+        loss = m.train_step(*batch)
+        assert np.allclose(loss, want_loss, rtol=1e-5, atol=0), (n_hot, loss, want_loss)
+        got[n_hot] = m.get_table("item_m")
+        assert np.abs(got[n_hot] - ref.mI).max() <= 1e-5 * scale, n_hot
+        assert np.array_equal(bits(m.get_table("user_embedding")), bits(ref.U)), n_hot      # the user rows are not touched by it
+        if n_hot == 28:
+            with pytest.raises(pda.PdaError, match="outside"):
+                m.set_hot_items([3, n_items])
+            with pytest.raises(pda.PdaError, match="twice"):
+                m.set_hot_items([3, 4, 3])
+        m.close()
+    assert np.abs(got[28] - got[0]).max() <= 2e-6 * scale        # only the summation order of the popular rows differs
 
 
 def test_host_batches_with_bad_ids_are_rejected(pda):

@@ -28,7 +28,7 @@ __device__ __forceinline__ void red4(float* p, float4 v) { asm volatile("red.glo
 // INTER = 0: U, M, V separate;  1: interleaved (U points at the [n][3][128] array).  MODE bit 0: do the stores, bit 1: do the reds
 template <int INTER, int D, int NW>
 __global__ void __launch_bounds__(NW * 32) skel(float* U, float* M, float* V, const float* I, float* GI, const int* iu, const int* ip,
-                                                  const int* in, int64_t B, int mode) {
+                                                  const int* in, int64_t B, int mode, int hot) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int STAGE = 5 * 512;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(NW * 32) skel(float* U, float* M, float* V, co
                 *reinterpret_cast<float4*>(V + u * 128 + lane * 4) = c;
             }
         }
-        if ((mode & 2) && !(mode & 4)) { red4(GI + pi * 128 + lane * 4, p); red4(GI + ni * 128 + lane * 4, n); }
+        if ((mode & 2) && !(mode & 4)) { if (pi >= hot) red4(GI + pi * 128 + lane * 4, p); red4(GI + ni * 128 + lane * 4, n); }   // hot: the `hot` most popular items' reductions are dropped (= an ideal privatised accumulator)
         if (mode & (4 | 8)) {
             // results back into this warp's out-staging rows (a second 2560 B area per warp), then bulk copies / bulk reduces
             const uint32_t ob = smem_u32(smem) + NW * D * STAGE + NW * D * 8 + 64 + warp * STAGE;
@@ -105,14 +105,14 @@ static uint64_t rng = 88172645463325252ull;
 static uint32_t xr() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return (uint32_t)(rng >> 16); }
 
 template <int INTER, int D, int NW>
-float run(float* U, float* M, float* V, float* I, float* GI, int* iu, int* ip, int* in, int64_t B, int mode, int ctas_per_sm) {
+float run(float* U, float* M, float* V, float* I, float* GI, int* iu, int* ip, int* in, int64_t B, int mode, int ctas_per_sm, int hot = 0) {
     const size_t smem = (size_t)NW * D * 2560 + NW * D * 8 + 64 + (size_t)NW * 2560;
     cudaFuncSetAttribute(skel<INTER, D, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
     float best = 1e9f;
     for (int it = 0; it < 4; ++it) {
         cudaEventRecord(e0);
-        skel<INTER, D, NW><<<148 * ctas_per_sm, NW * 32, smem>>>(U, M, V, I, GI, iu, ip, in, B, mode);
+        skel<INTER, D, NW><<<148 * ctas_per_sm, NW * 32, smem>>>(U, M, V, I, GI, iu, ip, in, B, mode, hot);
         cudaEventRecord(e1); cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (it && ms < best) best = ms;
@@ -141,10 +141,22 @@ int main(int argc, char** argv) {
         for (int64_t i = 0; i < B; ++i) { hu[i] = t[i].u; hp[i] = t[i].p; hn[i] = t[i].n; }
         printf("batch sorted by pos item\n");
     }
+    const int dist = argc > 2 ? atoi(argv[2]) : 0;
+    if (dist == 2) { for (int64_t i = 0; i < B; ++i) hp[i] = xr() % nI; printf("uniform positives\n"); }
     cudaMalloc(&iu, B * 4); cudaMalloc(&ip, B * 4); cudaMalloc(&in, B * 4);
     cudaMemcpy(iu, hu, B * 4, cudaMemcpyHostToDevice); cudaMemcpy(ip, hp, B * 4, cudaMemcpyHostToDevice); cudaMemcpy(in, hn, B * 4, cudaMemcpyHostToDevice);
     const double gb = B * (40.0 * 128 + 20) / 1e9;
     printf("B = 2^20 triples, %lld users, 1M items; algorithmic %.2f GB per launch (40d+20 per triple)\n", (long long)nU, gb);
+    if (dist >= 2) {   // how much of the reduction cost is same-row contention on the popular items?
+        const int hots[5] = {0, 32, 256, 4096, 1 << 30};
+        for (int k = 0; k < 5; ++k) {
+            long long kept = 0;
+            for (int64_t i = 0; i < B; ++i) kept += hp[i] >= hots[k];
+            printf("reds of positives with rank >= %d only (%lld of 2^20 kept): reads+reds %.3f ms, reads+stores+reds %.3f ms\n", hots[k], kept,
+                   run<0, 3, 8>(U, M, V, I, GI, iu, ip, in, B, 2, 3, hots[k]), run<0, 3, 8>(U, M, V, I, GI, iu, ip, in, B, 3, 3, hots[k]));
+        }
+        return 0;
+    }
     {
         // bulk variants (D = 2 stages + the out-staging area, 3 CTAs per SM): 1|4 = plain stores + bulk reduces, 8|2 = bulk stores + red.v4, 8|4 = both bulk
         const int modes[4] = {4, 1 | 4, 8 | 2, 8 | 4};

@@ -47,10 +47,14 @@ def main():
                 dict(PDA_STEP_PIPE="1", PDA_STEP_PIPE_D="4", PDA_STEP_PIPE_NW="4", PDA_STEP_PIPE_HINTS="1")]
     if a.variants:
         variants = [dict(kv.split("=") for kv in v.split(",")) for v in a.variants.split(";")]
+    top_items = torch.argsort(torch.bincount(ds["items"].to(torch.int64), minlength=a.items), descending=True)[:28].cpu().numpy()
     for v in variants:
+        v = dict(v)
+        if "HOT" in v:      # popular-item rows pre-summed in shared memory: how many (0 = none; default = the library's own list)
+            m.set_hot_items(top_items[:int(v["HOT"])])
         for k in ("PDA_STEP_PIPE", "PDA_STEP_PIPE_D", "PDA_STEP_PIPE_NW", "PDA_STEP_PIPE_HINTS", "PDA_STEP_PIPE_V"):
             os.environ.pop(k, None)
-        os.environ.update(v)
+        os.environ.update({k: x for k, x in v.items() if k != "HOT"})
         m.train_sampled(2020, 0, step, 5, B); step += 5
         m.synchronize()
         m.profile(True)
