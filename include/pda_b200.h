@@ -115,8 +115,8 @@ int pda_set_deterministic(pda_model* m, int on);
 /* Popular items of the step kernel: the gradient rows of these items (as POSITIVE item of a triple) are summed per thread
  * block in shared memory and reach the gradient accumulator once per block -- a Zipf head puts a quarter of a batch on a
  * few dozen rows, and same-row reductions serialise in L2.  A performance hint only (the sums are the same for any list;
- * d = 128 pipeline only).  pda_set_train_csr* installs the most frequent items of the train CSR (at most 28; the count
- * is $PDA_STEP_HOT, 0 = none); this call replaces the list (n = 0 clears it).  ids: host array, distinct. */
+ * d = 128 pipeline only).  pda_set_train_csr* installs the most frequent items of the train CSR (8 by default, at most 28:
+ * $PDA_STEP_HOT, 0 = none); this call replaces the list (n = 0 clears it).  ids: host array, distinct. */
 int pda_set_hot_items(pda_model* m, const int32_t* ids, int32_t n);
 /* out[0] = rows updated with a gradient by the lazy apply kernel, out[1] = zero-gradient row-steps replayed, both since
  * the last call with reset != 0 (synchronises the device) */

@@ -425,10 +425,10 @@ int pda_set_hot_items(pda_model* m, const int32_t* ids, int32_t n) {
     return PDA_OK;
 }
 
-// default hot list: the most frequent items of the train CSR ($PDA_STEP_HOT = how many, 0 = none; at most PDA_MAX_HOT_ITEMS)
+// default hot list: the most frequent items of the train CSR ($PDA_STEP_HOT = how many, default 8, 0 = none; at most PDA_MAX_HOT_ITEMS)
 static int hot_items_from_csr(pda_model* m) {
     const char* e = getenv("PDA_STEP_HOT");
-    int want = e ? atoi(e) : PDA_MAX_HOT_ITEMS;
+    int want = e ? atoi(e) : PDA_DEFAULT_HOT_ITEMS;
     if (want > PDA_MAX_HOT_ITEMS) want = PDA_MAX_HOT_ITEMS;
     if (want > m->nI) want = (int)m->nI;
     if (want <= 0 || m->nnz <= 0 || m->d != 128) return pda_set_hot_items(m, nullptr, 0);   // only the d = 128 pipeline uses it

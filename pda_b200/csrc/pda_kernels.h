@@ -43,6 +43,10 @@ struct StepArgs {
     const uint8_t* hot_slot; const int32_t* hot_ids; int n_hot;
 };
 constexpr int PDA_MAX_HOT_ITEMS = 28;   // 14 KB: what a 3-stage ring of 8 warps leaves of a third of an SM's shared memory
+// default list length.  Measured on the bench workload (value / e2e, M triples/s): 0 rows 482 / 494, 8 rows 494 / 506,
+// 16 rows 491 / 474, 28 rows 490 / 474 -- the first rows remove most of the same-address serialisation, and beyond 8 the
+// step kernel's CTAs fill the SM's shared memory, so the batch-check / copy-side kernels of the host path stop overlapping it
+constexpr int PDA_DEFAULT_HOT_ITEMS = 8;
 
 struct AdamArgs {
     float* W[4]; float* m[4]; float* v[4]; float* G[4];   // user table, item table, [user bias, item bias]

@@ -344,17 +344,20 @@ static int launch_pipe_inst(const StepArgs& a, int hints, cudaStream_t st) {
     const size_t ring = (size_t)NW * D * NR * sp::ROW_B + (size_t)NW * D * 8 + 16;
     const size_t per_cta = (size_t)(227 * 1024) / MINB - 1024;
     const int hot_cap = per_cta > ring ? (int)((per_cta - ring) / sp::ROW_B) : 0;
-    const int hot_rows = hot_cap < PDA_MAX_HOT_ITEMS ? hot_cap : PDA_MAX_HOT_ITEMS;   // constant per instantiation
-    const size_t smem = ring + (size_t)hot_rows * sp::ROW_B;
+    int n_hot = a.n_hot < PDA_MAX_HOT_ITEMS ? a.n_hot : PDA_MAX_HOT_ITEMS;
+    if (n_hot > hot_cap) n_hot = hot_cap;          // slots beyond the shared-memory rows keep the global reduction
+    const size_t smem = ring + (size_t)n_hot * sp::ROW_B;
     auto kern = bpr_step_pipe_kernel<MODE, FUSE, D, NW, MINB, V>;
-    static int ctas_per_sm = 0, n_sm = 0;
-    if (!ctas_per_sm) {
-        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return 1;
+    static int ctas_per_sm = 0, n_sm = 0, occ_for_hot = -1;
+    if (!ctas_per_sm || occ_for_hot != n_hot) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(ring + (size_t)hot_cap * sp::ROW_B)) != cudaSuccess)
+            return 1;
         int dev = 0, occ = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NW * 32, smem) != cudaSuccess || occ < 1) return 1;
         ctas_per_sm = occ;
+        occ_for_hot = n_hot;
     }
     // one resident wave; every CTA owns a contiguous, 32-aligned range of the batch
     int64_t grid = (int64_t)n_sm * ctas_per_sm;
@@ -364,7 +367,7 @@ static int launch_pipe_inst(const StepArgs& a, int hints, cudaStream_t st) {
     const int64_t seg = ((chunks + grid - 1) / grid) * 32;
     grid = (a.B + seg - 1) / seg;
     StepArgs b = a;
-    if (b.n_hot > hot_rows) b.n_hot = hot_rows;   // slots beyond the shared-memory rows keep the global reduction
+    b.n_hot = n_hot;
     kern<<<(int)grid, NW * 32, smem, st>>>(b, seg, hints);
     return 0;
 }
