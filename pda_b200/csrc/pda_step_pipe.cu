@@ -8,20 +8,20 @@
 //     The lane that holds a triple's ids issues cp.async.bulk (UBLKCP, 512 B per row) for the triple D positions
 //     ahead of the one being computed and arms the stage's mbarrier with the byte count; the warp waits on the
 //     mbarrier of the stage it consumes.  D x (3 or 5) x 512 B are in flight per warp while it computes -- the memory
-//     latency hides behind the (instruction-bound) exact Adam replay instead of adding to it.
+//     latency hides behind the (MUFU / FMA-pipe bound) exact Adam replay instead of adding to it.
 //   * ids / pops of 32 triples are loaded coalesced (lane l <- triple l of the chunk) one chunk ahead, together with
 //     applied[user]; per triple they reach the other lanes by shuffle.
 //   * a CTA owns a contiguous range of the batch and its warps draw 32-triple chunks from a shared-memory counter:
 //     the replay length of a user row is geometric (mean U/B), so static warp ranges would leave a tail.
-//   * L2 policy: user rows are touched once per step (3.2 GB of the step's traffic on the synthetic set) -> evict_first
-//     on their loads and stores; item rows and the item-gradient accumulator are Zipf-hot -> evict_last, so the hot
-//     head of the item table stays in the 126 MB L2.
+//   * L2 policies (`hints`: evict_first on the user rows, touched once per step; evict_last on the Zipf-hot item rows and
+//     accumulator) are implemented and measured slower (1.42 vs 1.34 ms): off by default.
 //   * the gradient rows of the n_hot most popular positive items (StepArgs::hot_slot) are summed per CTA in shared memory
 //     (CAS-loop fp32 atomics) and reach the accumulator once per CTA: 2^20 triples put 25 % of their positive-item rows on
 //     28 addresses, and same-address red.global.add serialises in L2 (tools/microbench/gather_bw: 1.14 -> 0.92 ms for the
 //     memory skeleton when those reductions disappear).
-//   * the exact replay runs with one range guard per block of 8 steps (pda_common.cuh), the row's own Adam step with
-//     one guard per float4, log(sigmoid + 1e-10) once per 32 triples (lane l <- triple l).
+//   * the exact replay runs with one warp-voted range guard per block of 16 steps, on the negated-v state (pda_common.cuh:
+//     lazy_replay4_warp), the row's own Adam step with one guard per float4; the two dot products finish on the two
+//     half-warps and elu runs once for both; log(sigmoid + 1e-10) once per 32 triples (lane l <- triple l).
 #include <stdlib.h>
 
 #include "pda_kernels.h"
