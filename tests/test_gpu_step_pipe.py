@@ -191,7 +191,7 @@ def test_popular_item_rows_summed_in_shared_memory(pda, c_oracle, train):
             with pytest.raises(pda.PdaError, match="twice"):
                 m.set_hot_items([3, 4, 3])
         m.close()
-    assert np.abs(got[28] - got[0]).max() <= 2e-6 * scale        # only the summation order of the popular rows differs
+    assert np.abs(got[28] - got[0]).max() <= 1e-5 * scale        # only the summation order of the popular rows differs (fp32 sums of up to ~400 rows)
 
 
 def test_host_batches_with_bad_ids_are_rejected(pda):
